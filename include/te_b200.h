@@ -1,0 +1,161 @@
+/*
+ * te_b200.h — C ABI of the B200-native traversability filter chain and footprint sweep.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++/torch types.  Each entry point
+ * names the reference interface it replaces (path:line relative to the reference repository
+ * leggedrobotics/traversability_estimation).  The reference-side binding a maintainer would add
+ * (the filters::FilterBase<grid_map::GridMap> plugin shells) is in
+ * traversability_estimation_b200/plugin/ and described in INTEGRATION.md.
+ *
+ * Layers are float32, column-major exactly like grid_map::Matrix (Eigen::MatrixXf):
+ * value(i, j) = data[j * rows + i]; NaN/Inf = invalid cell (GridMap::isValid == std::isfinite).
+ *
+ * Every function returns TE_OK (0) or a negative te_status; it never throws.  The message of the
+ * last failure on the calling thread is available from te_last_error().  There is NO CPU fallback:
+ * without a CUDA device every compute entry point fails with TE_ERR_CUDA.
+ */
+#ifndef TE_B200_H
+#define TE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TE_B200_ABI_VERSION 1
+
+typedef enum te_status {
+  TE_OK = 0,
+  TE_ERR_BAD_ARG = -1,       /* null pointer, non-positive size, invalid parameter value */
+  TE_ERR_MISSING_LAYER = -2, /* a required input layer pointer is null (reference: GridMap::at throws) */
+  TE_ERR_CUDA = -3,          /* CUDA runtime/driver failure, or no device */
+  TE_ERR_UNSUPPORTED = -4,   /* e.g. non-zero circular-buffer start index */
+  TE_ERR_NCCL = -5
+} te_status;
+
+/* Where the layer pointers passed to a call live. */
+typedef enum te_memory { TE_MEM_HOST = 0, TE_MEM_DEVICE = 1 } te_memory;
+
+/* grid_map::GridMap geometry, doubles exactly as the container holds them; needed bit-for-bit
+ * because CircleIterator decides window membership on absolute double positions.
+ * (grid_map_core GridMap::getSize/getResolution/getLength/getPosition/getStartIndex) */
+typedef struct te_geometry {
+  int32_t rows, cols;
+  double resolution;
+  double length_x, length_y;
+  double position_x, position_y;
+  int32_t start_row, start_col; /* must be 0: shells call convertToDefaultStartIndex first */
+} te_geometry;
+
+/* Column slab of a larger map (multi-GPU tiling, one slab per rank).  Inputs cover columns
+ * [col_begin - halo_left, col_begin + col_count + halo_right) of the global map; outputs cover
+ * [col_begin, col_begin + col_count).  Columns outside the global map need not exist.
+ * Pass NULL for "the whole map". */
+typedef struct te_slab {
+  int32_t col_begin, col_count;
+  int32_t halo_left, halo_right;
+} te_slab;
+
+enum { TE_NORMALS_FIXTURE = 0, TE_NORMALS_RAW_MOMENT = 1 };
+
+/* Parameters of the YAML chain (traversability_estimation/config/robot_filter_parameter.yaml:2-37);
+ * names follow the filters' own parameter names. */
+typedef struct te_chain_params {
+  double normals_radius;          /* NormalVectorsFilter `radius` (:8) */
+  int32_t normals_algorithm;      /* TE_NORMALS_* */
+  int32_t normals_positive_axis;  /* `normal_vector_positive_axis` 0=x 1=y 2=z (:9) */
+  double slope_critical;          /* SlopeFilter `critical_value` (:14), SlopeFilter.cpp:36-46 */
+  double step_critical;           /* StepFilter `critical_value` (:18), StepFilter.cpp:40-50 */
+  double step_first_radius;       /* `first_window_radius` (:19) */
+  double step_second_radius;      /* `second_window_radius` (:20) */
+  int32_t step_critical_cells;    /* `critical_cell_number` (:21) */
+  int32_t reserved0;
+  double roughness_critical;      /* RoughnessFilter `critical_value` (:26), RoughnessFilter.cpp:38-48 */
+  double roughness_radius;        /* `estimation_radius` (:27) */
+  float fuse_weight;              /* MathExpressionFilter (:29-33): weight*((slope+step)+roughness) in float32 */
+  int32_t reserved1;
+} te_chain_params;
+
+/* TraversabilityMap::traversabilityFootprint(radius, offset) and the members it reads. */
+typedef struct te_footprint_params {
+  double radius;                  /* = radiusMin; TraversabilityMap.cpp:313 */
+  double offset;                  /* radiusMax = radius + offset */
+  double traversability_default;  /* traversabilityDefault_ (robot_footprint_parameter.yaml:8) */
+  double max_gap_width;           /* maxGapWidth_ (robot.yaml:10) */
+  double critical_step_height;    /* criticalStepHeight_ (TraversabilityMap.cpp:117-126) */
+  int32_t radius_is_integer_norm; /* SpiralIterator::getCurrentRadius via Eigen integer norm (1) or exact (0) */
+  int32_t reserved0;
+} te_footprint_params;
+
+/* Which implementation te_chain uses. AUTO picks the fused stencil when the window shapes have a
+ * specialised instantiation, else the generic kernel; both compute the same layers. */
+typedef enum te_kernel { TE_KERNEL_AUTO = 0, TE_KERNEL_GENERIC = 1, TE_KERNEL_FUSED = 2 } te_kernel;
+
+typedef struct te_ctx te_ctx;
+
+/* Lifetime: one context per plugin instance / per rank.  Owns a non-blocking CUDA stream, the
+ * per-geometry position tables and staging buffers.  Thread-safe: one in-flight call per context. */
+int te_create(te_ctx** out, int device);
+int te_destroy(te_ctx* ctx);
+const char* te_last_error(void);
+int te_abi_version(void);
+
+/* Run subsequent calls on an external stream (cudaStream_t passed as void*; NULL restores the
+ * context's own stream).  Device-memory calls are asynchronous on that stream; te_synchronize waits. */
+int te_set_stream(te_ctx* ctx, void* cuda_stream);
+int te_synchronize(te_ctx* ctx);
+int te_set_kernel(te_ctx* ctx, int te_kernel_choice);
+/* Counters since creation: kernels launched, cells that took the certified slow path in the fused kernel. */
+int te_get_stats(te_ctx* ctx, int64_t* kernel_launches, int64_t* slow_path_cells);
+
+/* filters::SlopeFilter<grid_map::GridMap>::update — traversability_estimation_filters/src/SlopeFilter.cpp:59-89.
+ * in: surface_normal_z, out: the `map_type` layer. */
+int te_slope(te_ctx* ctx, const te_geometry* g, double critical_value, const float* surface_normal_z,
+             float* out, int memory);
+
+/* grid_map::NormalVectorsFilter::update (area method) — third-party, configured at
+ * robot_filter_parameter.yaml:3-9.  out: surface_normal_{x,y,z}. */
+int te_normals(te_ctx* ctx, const te_geometry* g, const te_chain_params* p, const float* elevation,
+               float* nx, float* ny, float* nz, int memory);
+
+/* filters::StepFilter<grid_map::GridMap>::update — StepFilter.cpp:102-182 (both passes; the
+ * temporary step_height layer never leaves the device). */
+int te_step(te_ctx* ctx, const te_geometry* g, const te_chain_params* p, const float* elevation,
+            float* out, int memory);
+
+/* filters::RoughnessFilter<grid_map::GridMap>::update — RoughnessFilter.cpp:73-132. */
+int te_roughness(te_ctx* ctx, const te_geometry* g, const te_chain_params* p, const float* elevation,
+                 const float* nx, const float* ny, const float* nz, float* out, int memory);
+
+/* The whole chain filters::FilterChain<grid_map::GridMap>::update runs at TraversabilityMap.cpp:214:
+ * normals -> slope, step, roughness -> weighted sum; normals are deleted unless pointers are given
+ * (DeletionFilter, robot_filter_parameter.yaml:34-37).  `slab` NULL = whole map. */
+int te_chain(te_ctx* ctx, const te_geometry* g, const te_slab* slab, const te_chain_params* p,
+             const float* elevation, float* slope, float* step, float* roughness, float* traversability,
+             float* nx_or_null, float* ny_or_null, float* nz_or_null, int memory);
+
+/* nmaps independent maps of identical geometry, stored back to back (map m at offset m*rows*cols). */
+int te_chain_batched(te_ctx* ctx, const te_geometry* g, const te_chain_params* p, int32_t nmaps,
+                     const float* elevation, float* slope, float* step, float* roughness,
+                     float* traversability, int memory);
+
+/* TraversabilityMap::traversabilityFootprint(const double& radius, const double& offset) —
+ * traversability_estimation/src/TraversabilityMap.cpp:307-318 with isTraversable (:654-746),
+ * isTraversableForFilters (:774-792), checkForStep (:794-865), checkForSlope (:867-893).
+ * out: traversability_footprint; slope_footprint/step_footprint memoisation layers optional. */
+int te_footprint(te_ctx* ctx, const te_geometry* g, const te_slab* slab, const te_footprint_params* p,
+                 const float* traversability, const float* slope, const float* step, const float* elevation,
+                 float* traversability_footprint, float* slope_footprint_or_null, float* step_footprint_or_null,
+                 int memory);
+
+/* CUDA IPC helpers so that a neighbour rank's slab can be read in place over NVLink. */
+int te_ipc_export(const void* device_ptr, void* handle_64_bytes);
+int te_ipc_open(const void* handle_64_bytes, void** device_ptr_out);
+int te_ipc_close(void* device_ptr);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,202 @@
+"""ctypes view of include/te_b200.h."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = os.path.join(_HERE, "libte_b200.so")
+
+MEM_HOST, MEM_DEVICE = 0, 1
+KERNEL_AUTO, KERNEL_GENERIC, KERNEL_FUSED = 0, 1, 2
+
+EXPORTS = ["te_create", "te_destroy", "te_last_error", "te_abi_version", "te_set_stream", "te_synchronize",
+           "te_set_kernel", "te_get_stats", "te_slope", "te_normals", "te_step", "te_roughness", "te_chain",
+           "te_chain_batched", "te_footprint", "te_ipc_export", "te_ipc_open", "te_ipc_close"]
+
+
+class TEError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"te_b200 error {code}: {msg}")
+        self.code = code
+
+
+class Geometry(C.Structure):
+    _fields_ = [("rows", C.c_int32), ("cols", C.c_int32), ("resolution", C.c_double),
+                ("length_x", C.c_double), ("length_y", C.c_double),
+                ("position_x", C.c_double), ("position_y", C.c_double),
+                ("start_row", C.c_int32), ("start_col", C.c_int32)]
+
+    @classmethod
+    def make(cls, rows, cols, resolution, position=(0.0, 0.0)):
+        # GridMap::setGeometry: length = size * resolution
+        return cls(rows, cols, resolution, rows * resolution, cols * resolution, position[0], position[1], 0, 0)
+
+
+class Slab(C.Structure):
+    _fields_ = [("col_begin", C.c_int32), ("col_count", C.c_int32), ("halo_left", C.c_int32), ("halo_right", C.c_int32)]
+
+
+class ChainParams(C.Structure):
+    _fields_ = [("normals_radius", C.c_double), ("normals_algorithm", C.c_int32),
+                ("normals_positive_axis", C.c_int32), ("slope_critical", C.c_double),
+                ("step_critical", C.c_double), ("step_first_radius", C.c_double),
+                ("step_second_radius", C.c_double), ("step_critical_cells", C.c_int32),
+                ("reserved0", C.c_int32), ("roughness_critical", C.c_double),
+                ("roughness_radius", C.c_double), ("fuse_weight", C.c_float), ("reserved1", C.c_int32)]
+
+    @classmethod
+    def yaml_defaults(cls, algorithm=0):
+        """traversability_estimation/config/robot_filter_parameter.yaml:2-37"""
+        return cls(0.05, algorithm, 2, 1.0, 0.12, 0.04, 0.04, 4, 0, 0.05, 0.05,
+                   np.float32(1.0) / np.float32(3.0), 0)
+
+
+class FootprintParams(C.Structure):
+    _fields_ = [("radius", C.c_double), ("offset", C.c_double), ("traversability_default", C.c_double),
+                ("max_gap_width", C.c_double), ("critical_step_height", C.c_double),
+                ("radius_is_integer_norm", C.c_int32), ("reserved0", C.c_int32)]
+
+    @classmethod
+    def yaml_defaults(cls):
+        """robot_footprint_parameter.yaml:5-8, robot.yaml:10, robot_filter_parameter.yaml:18"""
+        return cls(0.30, 0.15, 0.3, 0.3, 0.12, 1, 0)
+
+
+def library_path() -> str:
+    return _LIB
+
+
+def build_library(force: bool = False) -> str:
+    """nvcc-compile csrc/ for sm_100a into libte_b200.so (in-tree, travels to the GPU box)."""
+    args = ["make", "-C", os.path.join(_HERE, "csrc"), "-s"]
+    if force:
+        args.append("-B")
+    subprocess.check_call(args)
+    return _LIB
+
+
+_lib = None
+
+
+def load_library():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB):
+            raise ImportError(f"{_LIB} is missing: run traversability_estimation_b200.build_library() "
+                              "(there is no CPU fallback)")
+        L = C.CDLL(_LIB)
+        vp, fp = C.c_void_p, C.c_void_p  # layers are passed as raw addresses (host or device)
+        G, S = C.POINTER(Geometry), C.POINTER(Slab)
+        P, F = C.POINTER(ChainParams), C.POINTER(FootprintParams)
+        L.te_create.argtypes = [C.POINTER(vp), C.c_int]
+        L.te_destroy.argtypes = [vp]
+        L.te_last_error.restype = C.c_char_p
+        L.te_set_stream.argtypes = [vp, vp]
+        L.te_synchronize.argtypes = [vp]
+        L.te_set_kernel.argtypes = [vp, C.c_int]
+        L.te_get_stats.argtypes = [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+        L.te_slope.argtypes = [vp, G, C.c_double, fp, fp, C.c_int]
+        L.te_normals.argtypes = [vp, G, P, fp, fp, fp, fp, C.c_int]
+        L.te_step.argtypes = [vp, G, P, fp, fp, C.c_int]
+        L.te_roughness.argtypes = [vp, G, P, fp, fp, fp, fp, fp, C.c_int]
+        L.te_chain.argtypes = [vp, G, S, P, fp, fp, fp, fp, fp, fp, fp, fp, C.c_int]
+        L.te_chain_batched.argtypes = [vp, G, P, C.c_int32, fp, fp, fp, fp, fp, C.c_int]
+        L.te_footprint.argtypes = [vp, G, S, F, fp, fp, fp, fp, fp, fp, fp, C.c_int]
+        L.te_ipc_export.argtypes = [vp, vp]
+        L.te_ipc_open.argtypes = [vp, C.POINTER(vp)]
+        L.te_ipc_close.argtypes = [vp]
+        _lib = L
+    return _lib
+
+
+def _addr(a):
+    """Address of a numpy array (host) / torch tensor (device) / int / None."""
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return a
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data
+    if hasattr(a, "data_ptr"):
+        return a.data_ptr()
+    raise TypeError(type(a))
+
+
+class Context:
+    """One te_ctx (one per rank / plugin instance)."""
+
+    def __init__(self, device: int = 0):
+        self._L = load_library()
+        h = C.c_void_p()
+        self._check(self._L.te_create(C.byref(h), device))
+        self._h = h
+
+    def _check(self, rc):
+        if rc != 0:
+            raise TEError(rc, self._L.te_last_error().decode())
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.te_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_stream(self, stream_ptr):
+        self._check(self._L.te_set_stream(self._h, stream_ptr))
+
+    def synchronize(self):
+        self._check(self._L.te_synchronize(self._h))
+
+    def set_kernel(self, choice):
+        self._check(self._L.te_set_kernel(self._h, choice))
+
+    def stats(self):
+        a, b = C.c_int64(), C.c_int64()
+        self._check(self._L.te_get_stats(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def slope(self, g, critical, nz, out, memory):
+        self._check(self._L.te_slope(self._h, C.byref(g), critical, _addr(nz), _addr(out), memory))
+
+    def normals(self, g, p, elevation, nx, ny, nz, memory):
+        self._check(self._L.te_normals(self._h, C.byref(g), C.byref(p), _addr(elevation), _addr(nx), _addr(ny), _addr(nz), memory))
+
+    def step(self, g, p, elevation, out, memory):
+        self._check(self._L.te_step(self._h, C.byref(g), C.byref(p), _addr(elevation), _addr(out), memory))
+
+    def roughness(self, g, p, elevation, nx, ny, nz, out, memory):
+        self._check(self._L.te_roughness(self._h, C.byref(g), C.byref(p), _addr(elevation), _addr(nx), _addr(ny), _addr(nz),
+                                         _addr(out), memory))
+
+    def chain(self, g, p, elevation, slope, step, roughness, traversability, memory, slab=None, nx=None, ny=None, nz=None):
+        self._check(self._L.te_chain(self._h, C.byref(g), C.byref(slab) if slab is not None else None, C.byref(p),
+                                     _addr(elevation), _addr(slope), _addr(step), _addr(roughness), _addr(traversability),
+                                     _addr(nx), _addr(ny), _addr(nz), memory))
+
+    def chain_batched(self, g, p, nmaps, elevation, slope, step, roughness, traversability, memory):
+        self._check(self._L.te_chain_batched(self._h, C.byref(g), C.byref(p), nmaps, _addr(elevation), _addr(slope),
+                                             _addr(step), _addr(roughness), _addr(traversability), memory))
+
+    def footprint(self, g, fp, traversability, slope, step, elevation, out, memory, slab=None, slope_fp=None, step_fp=None):
+        self._check(self._L.te_footprint(self._h, C.byref(g), C.byref(slab) if slab is not None else None, C.byref(fp),
+                                         _addr(traversability), _addr(slope), _addr(step), _addr(elevation), _addr(out),
+                                         _addr(slope_fp), _addr(step_fp), memory))
+
+    # Convenience for host numpy layers (column-major float32), used by tests.
+    def chain_host(self, g, p, elevation, with_normals=False):
+        e = np.asfortranarray(elevation, dtype=np.float32)
+        assert e.shape == (g.rows, g.cols)
+        o = {k: np.empty((g.rows, g.cols), np.float32, order="F") for k in ("slope", "step", "roughness", "traversability")}
+        n = {k: np.empty((g.rows, g.cols), np.float32, order="F") for k in ("nx", "ny", "nz")} if with_normals else {}
+        self.chain(g, p, e, o["slope"], o["step"], o["roughness"], o["traversability"], MEM_HOST, **n)
+        o.update(n)
+        return o

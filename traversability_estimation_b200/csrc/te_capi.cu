@@ -1,0 +1,591 @@
+// te_capi.cu — the extern "C" boundary of libte_b200 (see include/te_b200.h).
+// Host-side responsibilities only: argument validation with the reference's conventions, the
+// per-geometry position tables, host<->device staging for TE_MEM_HOST callers, kernel selection.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/te_b200.h"
+#include "te_kernels.h"
+#include "te_fused.h"
+#include "te_footprint.h"
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+  return code;
+}
+
+#define TE_CUDA(expr)                                                                              \
+  do {                                                                                             \
+    cudaError_t e__ = (expr);                                                                      \
+    if (e__ != cudaSuccess) return fail(TE_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e__)); \
+  } while (0)
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e == cudaSuccess) cap = bytes;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+// grid_map::getPositionFromIndex operand order.
+inline double cell_coord(double map_pos, double length, double res, int idx) {
+  const double offset = 0.5 * length - 0.5 * res;
+  return (map_pos + offset) + res * (-(double)idx);
+}
+
+// Largest index offset that can satisfy the circle test, plus a guard cell.
+inline int reach_generous(double radius, double res) { return (int)std::floor(radius / res) + 1; }
+// Dependency radius in cells (what a slab halo must provide).
+inline int reach_true(double radius, double res) { return (int)std::floor(radius / res + 1e-9); }
+
+}  // namespace
+
+struct te_ctx {
+  int device = 0;
+  int sms = 148;
+  cudaStream_t own_stream = nullptr;
+  cudaStream_t stream = nullptr;
+  std::mutex mu;
+  int kernel_choice = TE_KERNEL_AUTO;
+  int64_t launches = 0;
+  int64_t slow_cells = 0;
+
+  te_geometry geo{};
+  bool have_geo = false;
+  DevBuf dX, dY;
+  std::vector<double> hX, hY;
+
+  DevBuf stage[12];          // TE_MEM_HOST staging: 0..3 inputs, 4..11 outputs
+  DevBuf worklist, counter;  // fused-kernel fix-up list
+  te::FusedState fused;      // tensor maps / tables of the fused stencil
+  te::FootprintState fp;
+};
+
+namespace {
+
+int check_geometry(const te_geometry* g) {
+  if (!g) return fail(TE_ERR_BAD_ARG, "geometry is null");
+  if (g->rows <= 0 || g->cols <= 0) return fail(TE_ERR_BAD_ARG, "map size must be positive (rows=%d cols=%d)", g->rows, g->cols);
+  if (!(g->resolution > 0.0) || !std::isfinite(g->resolution)) return fail(TE_ERR_BAD_ARG, "resolution must be positive");
+  if (g->start_row != 0 || g->start_col != 0)
+    return fail(TE_ERR_UNSUPPORTED, "circular-buffer start index (%d,%d) != (0,0): call convertToDefaultStartIndex() first",
+                g->start_row, g->start_col);
+  if ((long long)g->rows * g->cols > 0x7fffffffLL * 2) return fail(TE_ERR_UNSUPPORTED, "map has more than 2^32 cells");
+  return TE_OK;
+}
+
+// Same validation as the filters' configure(): SlopeFilter.cpp:41, StepFilter.cpp:45,58,71,84,
+// RoughnessFilter.cpp:43,55.
+int check_params(const te_chain_params* p) {
+  if (!p) return fail(TE_ERR_BAD_ARG, "chain parameters are null");
+  if (!(p->normals_radius >= 0.0)) return fail(TE_ERR_BAD_ARG, "normals radius must be >= 0");
+  if (p->normals_algorithm != TE_NORMALS_FIXTURE && p->normals_algorithm != TE_NORMALS_RAW_MOMENT)
+    return fail(TE_ERR_BAD_ARG, "unknown normals algorithm %d", p->normals_algorithm);
+  if (p->normals_positive_axis < 0 || p->normals_positive_axis > 2) return fail(TE_ERR_BAD_ARG, "positive axis must be 0, 1 or 2");
+  if (p->slope_critical > M_PI_2 || p->slope_critical < 0.0 || std::isnan(p->slope_critical))
+    return fail(TE_ERR_BAD_ARG, "Critical slope must be in the interval [0, PI/2]");
+  if (!(p->step_critical >= 0.0)) return fail(TE_ERR_BAD_ARG, "Critical step height must be greater than zero");
+  if (!(p->step_first_radius >= 0.0) || !(p->step_second_radius >= 0.0))
+    return fail(TE_ERR_BAD_ARG, "step window radii must be greater than zero");
+  if (p->step_critical_cells <= 0) return fail(TE_ERR_BAD_ARG, "Number of critical cells must be greater than zero");
+  if (!(p->roughness_critical >= 0.0)) return fail(TE_ERR_BAD_ARG, "Critical roughness must be greater than zero");
+  if (!(p->roughness_radius >= 0.0)) return fail(TE_ERR_BAD_ARG, "Roughness estimation radius must be greater than zero");
+  return TE_OK;
+}
+
+int ensure_geometry(te_ctx* c, const te_geometry* g) {
+  if (c->have_geo && std::memcmp(&c->geo, g, sizeof(te_geometry)) == 0) return TE_OK;
+  c->hX.resize(g->rows);
+  c->hY.resize(g->cols);
+  for (int i = 0; i < g->rows; ++i) c->hX[i] = cell_coord(g->position_x, g->length_x, g->resolution, i);
+  for (int j = 0; j < g->cols; ++j) c->hY[j] = cell_coord(g->position_y, g->length_y, g->resolution, j);
+  TE_CUDA(c->dX.reserve(sizeof(double) * g->rows));
+  TE_CUDA(c->dY.reserve(sizeof(double) * g->cols));
+  // The tables may still be in use by kernels queued on the stream: order the overwrite after them.
+  TE_CUDA(cudaMemcpyAsync(c->dX.p, c->hX.data(), sizeof(double) * g->rows, cudaMemcpyHostToDevice, c->stream));
+  TE_CUDA(cudaMemcpyAsync(c->dY.p, c->hY.data(), sizeof(double) * g->cols, cudaMemcpyHostToDevice, c->stream));
+  TE_CUDA(cudaStreamSynchronize(c->stream));  // hX/hY are reused
+  c->geo = *g;
+  c->have_geo = true;
+  c->fused.invalidate();
+  c->fp.invalidate();
+  return TE_OK;
+}
+
+te::ChainDev make_chain_dev(const te_geometry* g, const te_chain_params* p) {
+  te::ChainDev d{};
+  const double res = g->resolution;
+  d.rn = p->normals_radius; d.rn2 = d.rn * d.rn; d.Rn = reach_generous(d.rn, res);
+  d.alg = p->normals_algorithm; d.axis = p->normals_positive_axis;
+  d.slope_crit = p->slope_critical;
+  d.step_crit = p->step_critical;
+  d.r1 = p->step_first_radius; d.r1sq = d.r1 * d.r1; d.R1 = reach_generous(d.r1, res);
+  d.r2 = p->step_second_radius; d.r2sq = d.r2 * d.r2; d.R2 = reach_generous(d.r2, res);
+  d.ncrit = p->step_critical_cells;
+  d.rough_crit = p->roughness_critical;
+  d.rr = p->roughness_radius; d.rr2 = d.rr * d.rr; d.Rr = reach_generous(d.rr, res);
+  d.fuse_w = p->fuse_weight;
+  return d;
+}
+
+int chain_halo(const te_geometry* g, const te_chain_params* p) {
+  const double res = g->resolution;
+  const int hn = reach_true(p->normals_radius, res), hr = reach_true(p->roughness_radius, res);
+  const int hs = reach_true(p->step_first_radius, res) + reach_true(p->step_second_radius, res);
+  return std::max(hn, std::max(hr, hs));
+}
+
+int resolve_slab(const te_geometry* g, const te_slab* s, int need_halo, te_slab* out) {
+  if (!s) {
+    *out = te_slab{0, g->cols, 0, 0};
+    return TE_OK;
+  }
+  if (s->col_begin < 0 || s->col_count <= 0 || s->col_begin + s->col_count > g->cols)
+    return fail(TE_ERR_BAD_ARG, "slab columns [%d,%d) outside map of %d columns", s->col_begin, s->col_begin + s->col_count, g->cols);
+  if (s->halo_left < 0 || s->halo_right < 0 || s->halo_left > s->col_begin || s->halo_right > g->cols - (s->col_begin + s->col_count))
+    return fail(TE_ERR_BAD_ARG, "slab halo (%d,%d) reaches outside the map", s->halo_left, s->halo_right);
+  const int need_l = std::min(need_halo, s->col_begin);
+  const int need_r = std::min(need_halo, g->cols - (s->col_begin + s->col_count));
+  if (s->halo_left < need_l || s->halo_right < need_r)
+    return fail(TE_ERR_BAD_ARG, "slab halo (%d,%d) smaller than the dependency radius %d of these parameters", s->halo_left,
+                s->halo_right, need_halo);
+  *out = *s;
+  return TE_OK;
+}
+
+te::SlabView make_view(te_ctx* c, const te_geometry* g, const te_slab& s) {
+  te::SlabView v{};
+  v.rows = g->rows;
+  v.cols_total = g->cols;
+  v.in_col0 = s.col_begin - s.halo_left;
+  v.in_ncols = s.halo_left + s.col_count + s.halo_right;
+  v.out_col0 = s.col_begin;
+  v.out_ncols = s.col_count;
+  v.X = (const double*)c->dX.p;
+  v.Y = (const double*)c->dY.p;
+  v.res = g->resolution;
+  return v;
+}
+
+struct Guard {
+  te_ctx* c;
+  int prev = -1;
+  bool ok = false;
+  explicit Guard(te_ctx* ctx) : c(ctx) {
+    c->mu.lock();
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    ok = cudaSetDevice(c->device) == cudaSuccess;
+  }
+  ~Guard() {
+    if (prev >= 0 && prev != c->device) cudaSetDevice(prev);
+    c->mu.unlock();
+  }
+};
+
+#define TE_ENTER(ctx)                                                   \
+  if (!(ctx)) return fail(TE_ERR_BAD_ARG, "context is null");           \
+  Guard guard__(ctx);                                                   \
+  if (!guard__.ok) return fail(TE_ERR_CUDA, "cudaSetDevice(%d) failed", (ctx)->device)
+
+int launch_check(te_ctx* c, const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(TE_ERR_CUDA, "%s launch failed: %s", what, cudaGetErrorString(e));
+  ++c->launches;
+  return TE_OK;
+}
+
+// Device-memory chain on one slab: picks the kernel.
+int run_chain_device(te_ctx* c, const te_geometry* g, const te_slab& s, const te_chain_params* p, const float* elev,
+                     const te::ChainOut& o, int nmaps) {
+  const te::SlabView v = make_view(c, g, s);
+  const te::ChainDev d = make_chain_dev(g, p);
+  bool use_fused = false;
+  if (c->kernel_choice != TE_KERNEL_GENERIC) {
+    use_fused = te::fused_eligible(c->fused, c->hX, c->hY, g, p);
+    if (!use_fused && c->kernel_choice == TE_KERNEL_FUSED)
+      return fail(TE_ERR_UNSUPPORTED, "fused stencil has no instantiation for these window shapes: %s", c->fused.why.c_str());
+  }
+  const size_t in_stride = (size_t)g->rows * v.in_ncols, out_stride = (size_t)g->rows * v.out_ncols;
+  if (use_fused) {
+    const unsigned cap = (unsigned)std::min<size_t>(out_stride, (size_t)1 << 26);
+    TE_CUDA(c->worklist.reserve(sizeof(unsigned) * (size_t)cap));
+    TE_CUDA(c->counter.reserve(sizeof(unsigned) * 4));
+    for (int m = 0; m < nmaps; ++m) {
+      te::ChainOut om = o;
+      om.slope += m * out_stride; om.step += m * out_stride; om.rough += m * out_stride; om.trav += m * out_stride;
+      if (om.nx) om.nx += m * out_stride;
+      if (om.ny) om.ny += m * out_stride;
+      if (om.nz) om.nz += m * out_stride;
+      TE_CUDA(cudaMemsetAsync(c->counter.p, 0, sizeof(unsigned) * 4, c->stream));
+      int rc = te::launch_chain_fused(c->fused, v, d, elev + m * in_stride, om, (unsigned*)c->worklist.p,
+                                      (unsigned*)c->counter.p, cap, c->sms, c->stream);
+      if (rc != 0) return fail(TE_ERR_CUDA, "fused chain launch failed: %s", c->fused.why.c_str());
+      if (int r2 = launch_check(c, "k_chain_fused")) return r2;
+      te::launch_fixup(v, d, elev + m * in_stride, om, (const unsigned*)c->worklist.p, (const unsigned*)c->counter.p, cap, c->sms,
+                       c->stream);
+      if (int r2 = launch_check(c, "k_fixup_cells")) return r2;
+    }
+  } else {
+    for (int m = 0; m < nmaps; ++m) {
+      te::ChainOut om = o;
+      om.slope += m * out_stride; om.step += m * out_stride; om.rough += m * out_stride; om.trav += m * out_stride;
+      if (om.nx) om.nx += m * out_stride;
+      if (om.ny) om.ny += m * out_stride;
+      if (om.nz) om.nz += m * out_stride;
+      te::launch_chain_generic(v, d, elev + m * in_stride, om, c->sms, c->stream);
+      if (int r2 = launch_check(c, "k_chain_generic")) return r2;
+    }
+  }
+  return TE_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int te_abi_version(void) { return TE_B200_ABI_VERSION; }
+
+const char* te_last_error(void) { return g_last_error.c_str(); }
+
+int te_create(te_ctx** out, int device) {
+  if (!out) return fail(TE_ERR_BAD_ARG, "out pointer is null");
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n <= 0)
+    return fail(TE_ERR_CUDA, "no CUDA device available (%s); libte_b200 has no CPU fallback", e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+  if (device < 0 || device >= n) return fail(TE_ERR_BAD_ARG, "device %d out of range [0,%d)", device, n);
+  int prev = 0;
+  cudaGetDevice(&prev);
+  TE_CUDA(cudaSetDevice(device));
+  te_ctx* c = new te_ctx();
+  c->device = device;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) c->sms = prop.multiProcessorCount;
+  e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) {
+    delete c;
+    cudaSetDevice(prev);
+    return fail(TE_ERR_CUDA, "cudaStreamCreate failed: %s", cudaGetErrorString(e));
+  }
+  c->stream = c->own_stream;
+  cudaSetDevice(prev);
+  *out = c;
+  return TE_OK;
+}
+
+int te_destroy(te_ctx* c) {
+  if (!c) return TE_OK;
+  {
+    Guard g(c);
+    if (g.ok) {
+      cudaStreamSynchronize(c->stream);
+      c->dX.release();
+      c->dY.release();
+      for (auto& b : c->stage) b.release();
+      c->worklist.release();
+      c->counter.release();
+      c->fused.release();
+      c->fp.release();
+      if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    }
+  }
+  delete c;
+  return TE_OK;
+}
+
+int te_set_stream(te_ctx* c, void* s) {
+  TE_ENTER(c);
+  c->stream = s ? (cudaStream_t)s : c->own_stream;
+  return TE_OK;
+}
+
+int te_synchronize(te_ctx* c) {
+  TE_ENTER(c);
+  TE_CUDA(cudaStreamSynchronize(c->stream));
+  return TE_OK;
+}
+
+int te_set_kernel(te_ctx* c, int choice) {
+  TE_ENTER(c);
+  if (choice < TE_KERNEL_AUTO || choice > TE_KERNEL_FUSED) return fail(TE_ERR_BAD_ARG, "unknown kernel choice %d", choice);
+  c->kernel_choice = choice;
+  return TE_OK;
+}
+
+int te_get_stats(te_ctx* c, int64_t* launches, int64_t* slow) {
+  TE_ENTER(c);
+  if (launches) *launches = c->launches;
+  if (slow) {
+    // the fix-up counter of the last fused launch (device word 0); cumulative host tally otherwise
+    unsigned last[4] = {0, 0, 0, 0};
+    if (c->counter.p) {
+      TE_CUDA(cudaStreamSynchronize(c->stream));
+      TE_CUDA(cudaMemcpy(last, c->counter.p, sizeof(last), cudaMemcpyDeviceToHost));
+    }
+    *slow = (int64_t)last[0];
+  }
+  return TE_OK;
+}
+
+int te_slope(te_ctx* c, const te_geometry* g, double crit, const float* nz, float* out, int memory) {
+  TE_ENTER(c);
+  if (int rc = check_geometry(g)) return rc;
+  if (crit > M_PI_2 || crit < 0.0 || std::isnan(crit)) return fail(TE_ERR_BAD_ARG, "Critical slope must be in the interval [0, PI/2]");
+  if (!nz) return fail(TE_ERR_MISSING_LAYER, "layer surface_normal_z is missing");
+  if (!out) return fail(TE_ERR_BAD_ARG, "output layer is null");
+  const long long n = (long long)g->rows * g->cols;
+  const size_t bytes = sizeof(float) * (size_t)n;
+  const float* din = nz;
+  float* dout = out;
+  if (memory == TE_MEM_HOST) {
+    TE_CUDA(c->stage[0].reserve(bytes));
+    TE_CUDA(c->stage[4].reserve(bytes));
+    TE_CUDA(cudaMemcpyAsync(c->stage[0].p, nz, bytes, cudaMemcpyHostToDevice, c->stream));
+    din = (const float*)c->stage[0].p;
+    dout = (float*)c->stage[4].p;
+  }
+  te::launch_slope(n, crit, din, dout, c->sms, c->stream);
+  if (int rc = launch_check(c, "k_slope")) return rc;
+  if (memory == TE_MEM_HOST) {
+    TE_CUDA(cudaMemcpyAsync(out, dout, bytes, cudaMemcpyDeviceToHost, c->stream));
+    TE_CUDA(cudaStreamSynchronize(c->stream));
+  }
+  return TE_OK;
+}
+
+int te_normals(te_ctx* c, const te_geometry* g, const te_chain_params* p, const float* elev, float* nx, float* ny, float* nz, int memory) {
+  TE_ENTER(c);
+  if (int rc = check_geometry(g)) return rc;
+  if (int rc = check_params(p)) return rc;
+  if (!elev) return fail(TE_ERR_MISSING_LAYER, "layer elevation is missing");
+  if (!nx || !ny || !nz) return fail(TE_ERR_BAD_ARG, "output layer is null");
+  if (int rc = ensure_geometry(c, g)) return rc;
+  const size_t bytes = sizeof(float) * (size_t)g->rows * g->cols;
+  const float* din = elev;
+  float* o[3] = {nx, ny, nz};
+  if (memory == TE_MEM_HOST) {
+    TE_CUDA(c->stage[0].reserve(bytes));
+    TE_CUDA(cudaMemcpyAsync(c->stage[0].p, elev, bytes, cudaMemcpyHostToDevice, c->stream));
+    din = (const float*)c->stage[0].p;
+    for (int k = 0; k < 3; ++k) {
+      TE_CUDA(c->stage[4 + k].reserve(bytes));
+      o[k] = (float*)c->stage[4 + k].p;
+    }
+  }
+  te_slab s{0, g->cols, 0, 0};
+  te::launch_normals(make_view(c, g, s), make_chain_dev(g, p), din, o[0], o[1], o[2], c->sms, c->stream);
+  if (int rc = launch_check(c, "k_normals")) return rc;
+  if (memory == TE_MEM_HOST) {
+    float* h[3] = {nx, ny, nz};
+    for (int k = 0; k < 3; ++k) TE_CUDA(cudaMemcpyAsync(h[k], o[k], bytes, cudaMemcpyDeviceToHost, c->stream));
+    TE_CUDA(cudaStreamSynchronize(c->stream));
+  }
+  return TE_OK;
+}
+
+int te_step(te_ctx* c, const te_geometry* g, const te_chain_params* p, const float* elev, float* out, int memory) {
+  TE_ENTER(c);
+  if (int rc = check_geometry(g)) return rc;
+  if (int rc = check_params(p)) return rc;
+  if (!elev) return fail(TE_ERR_MISSING_LAYER, "layer elevation is missing");
+  if (!out) return fail(TE_ERR_BAD_ARG, "output layer is null");
+  if (int rc = ensure_geometry(c, g)) return rc;
+  const size_t bytes = sizeof(float) * (size_t)g->rows * g->cols;
+  const float* din = elev;
+  float* dout = out;
+  if (memory == TE_MEM_HOST) {
+    TE_CUDA(c->stage[0].reserve(bytes));
+    TE_CUDA(c->stage[4].reserve(bytes));
+    TE_CUDA(cudaMemcpyAsync(c->stage[0].p, elev, bytes, cudaMemcpyHostToDevice, c->stream));
+    din = (const float*)c->stage[0].p;
+    dout = (float*)c->stage[4].p;
+  }
+  te_slab s{0, g->cols, 0, 0};
+  te::launch_step(make_view(c, g, s), make_chain_dev(g, p), din, dout, c->sms, c->stream);
+  if (int rc = launch_check(c, "k_step")) return rc;
+  if (memory == TE_MEM_HOST) {
+    TE_CUDA(cudaMemcpyAsync(out, dout, bytes, cudaMemcpyDeviceToHost, c->stream));
+    TE_CUDA(cudaStreamSynchronize(c->stream));
+  }
+  return TE_OK;
+}
+
+int te_roughness(te_ctx* c, const te_geometry* g, const te_chain_params* p, const float* elev, const float* nx, const float* ny,
+                 const float* nz, float* out, int memory) {
+  TE_ENTER(c);
+  if (int rc = check_geometry(g)) return rc;
+  if (int rc = check_params(p)) return rc;
+  if (!elev) return fail(TE_ERR_MISSING_LAYER, "layer elevation is missing");
+  if (!nx || !ny || !nz) return fail(TE_ERR_MISSING_LAYER, "layer surface_normal_{x,y,z} is missing");
+  if (!out) return fail(TE_ERR_BAD_ARG, "output layer is null");
+  if (int rc = ensure_geometry(c, g)) return rc;
+  const size_t bytes = sizeof(float) * (size_t)g->rows * g->cols;
+  const float* in[4] = {elev, nx, ny, nz};
+  float* dout = out;
+  if (memory == TE_MEM_HOST) {
+    for (int k = 0; k < 4; ++k) {
+      TE_CUDA(c->stage[k].reserve(bytes));
+      TE_CUDA(cudaMemcpyAsync(c->stage[k].p, in[k], bytes, cudaMemcpyHostToDevice, c->stream));
+      in[k] = (const float*)c->stage[k].p;
+    }
+    TE_CUDA(c->stage[4].reserve(bytes));
+    dout = (float*)c->stage[4].p;
+  }
+  te_slab s{0, g->cols, 0, 0};
+  te::launch_roughness(make_view(c, g, s), make_chain_dev(g, p), in[0], in[1], in[2], in[3], dout, c->sms, c->stream);
+  if (int rc = launch_check(c, "k_roughness")) return rc;
+  if (memory == TE_MEM_HOST) {
+    TE_CUDA(cudaMemcpyAsync(out, dout, bytes, cudaMemcpyDeviceToHost, c->stream));
+    TE_CUDA(cudaStreamSynchronize(c->stream));
+  }
+  return TE_OK;
+}
+
+static int chain_common(te_ctx* c, const te_geometry* g, const te_slab* slab, const te_chain_params* p, int nmaps, const float* elev,
+                        float* slope, float* step, float* rough, float* trav, float* nx, float* ny, float* nz, int memory) {
+  if (int rc = check_geometry(g)) return rc;
+  if (int rc = check_params(p)) return rc;
+  if (nmaps <= 0) return fail(TE_ERR_BAD_ARG, "number of maps must be positive");
+  if (!elev) return fail(TE_ERR_MISSING_LAYER, "layer elevation is missing");
+  if (!slope || !step || !rough || !trav) return fail(TE_ERR_BAD_ARG, "output layer is null");
+  te_slab s;
+  if (int rc = resolve_slab(g, slab, chain_halo(g, p), &s)) return rc;
+  if (int rc = ensure_geometry(c, g)) return rc;
+  const size_t in_bytes = sizeof(float) * (size_t)g->rows * (s.halo_left + s.col_count + s.halo_right) * nmaps;
+  const size_t out_bytes = sizeof(float) * (size_t)g->rows * s.col_count * nmaps;
+  te::ChainOut o{slope, step, rough, trav, nx, ny, nz};
+  const float* din = elev;
+  float* host_out[7] = {slope, step, rough, trav, nx, ny, nz};
+  if (memory == TE_MEM_HOST) {
+    TE_CUDA(c->stage[0].reserve(in_bytes));
+    TE_CUDA(cudaMemcpyAsync(c->stage[0].p, elev, in_bytes, cudaMemcpyHostToDevice, c->stream));
+    din = (const float*)c->stage[0].p;
+    float** dev_out[7] = {&o.slope, &o.step, &o.rough, &o.trav, &o.nx, &o.ny, &o.nz};
+    for (int k = 0; k < 7; ++k) {
+      if (!host_out[k]) continue;
+      TE_CUDA(c->stage[4 + k].reserve(out_bytes));
+      *dev_out[k] = (float*)c->stage[4 + k].p;
+    }
+  }
+  if (int rc = run_chain_device(c, g, s, p, din, o, nmaps)) return rc;
+  if (memory == TE_MEM_HOST) {
+    float* dev_out[7] = {o.slope, o.step, o.rough, o.trav, o.nx, o.ny, o.nz};
+    for (int k = 0; k < 7; ++k)
+      if (host_out[k]) TE_CUDA(cudaMemcpyAsync(host_out[k], dev_out[k], out_bytes, cudaMemcpyDeviceToHost, c->stream));
+    TE_CUDA(cudaStreamSynchronize(c->stream));
+  }
+  return TE_OK;
+}
+
+int te_chain(te_ctx* c, const te_geometry* g, const te_slab* slab, const te_chain_params* p, const float* elev, float* slope,
+             float* step, float* rough, float* trav, float* nx, float* ny, float* nz, int memory) {
+  TE_ENTER(c);
+  return chain_common(c, g, slab, p, 1, elev, slope, step, rough, trav, nx, ny, nz, memory);
+}
+
+int te_chain_batched(te_ctx* c, const te_geometry* g, const te_chain_params* p, int32_t nmaps, const float* elev, float* slope,
+                     float* step, float* rough, float* trav, int memory) {
+  TE_ENTER(c);
+  return chain_common(c, g, nullptr, p, nmaps, elev, slope, step, rough, trav, nullptr, nullptr, nullptr, memory);
+}
+
+int te_footprint(te_ctx* c, const te_geometry* g, const te_slab* slab, const te_footprint_params* p, const float* trav,
+                 const float* slope, const float* step, const float* elev, float* out, float* slope_fp, float* step_fp, int memory) {
+  TE_ENTER(c);
+  if (int rc = check_geometry(g)) return rc;
+  if (!p) return fail(TE_ERR_BAD_ARG, "footprint parameters are null");
+  if (!(p->radius >= 0.0) || !(p->offset >= 0.0)) return fail(TE_ERR_BAD_ARG, "footprint radius/offset must be >= 0");
+  if (!trav) return fail(TE_ERR_MISSING_LAYER, "layer traversability is missing");
+  if (!slope) return fail(TE_ERR_MISSING_LAYER, "layer traversability_slope is missing");
+  if (!step) return fail(TE_ERR_MISSING_LAYER, "layer traversability_step is missing");
+  if (!elev) return fail(TE_ERR_MISSING_LAYER, "layer elevation is missing");
+  if (!out) return fail(TE_ERR_BAD_ARG, "output layer is null");
+  te_slab s;
+  const int need = te::footprint_halo(g, p);
+  if (int rc = resolve_slab(g, slab, need, &s)) return rc;
+  if (int rc = ensure_geometry(c, g)) return rc;
+  const size_t in_bytes = sizeof(float) * (size_t)g->rows * (s.halo_left + s.col_count + s.halo_right);
+  const size_t out_bytes = sizeof(float) * (size_t)g->rows * s.col_count;
+  const float* in[4] = {trav, slope, step, elev};
+  float* o[3] = {out, slope_fp, step_fp};
+  float* host_o[3] = {out, slope_fp, step_fp};
+  if (memory == TE_MEM_HOST) {
+    for (int k = 0; k < 4; ++k) {
+      TE_CUDA(c->stage[k].reserve(in_bytes));
+      TE_CUDA(cudaMemcpyAsync(c->stage[k].p, in[k], in_bytes, cudaMemcpyHostToDevice, c->stream));
+      in[k] = (const float*)c->stage[k].p;
+    }
+    for (int k = 0; k < 3; ++k) {
+      if (!host_o[k]) continue;
+      TE_CUDA(c->stage[4 + k].reserve(out_bytes));
+      o[k] = (float*)c->stage[4 + k].p;
+    }
+  }
+  const te::SlabView v = make_view(c, g, s);
+  int nl = 0;
+  int rc = te::launch_footprint(c->fp, v, g, p, c->hX, c->hY, in[0], in[1], in[2], in[3], o[0], o[1], o[2], c->sms, c->stream, &nl);
+  if (rc != 0) return fail(rc, "footprint sweep failed: %s", c->fp.why.c_str());
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(TE_ERR_CUDA, "footprint launch failed: %s", cudaGetErrorString(e));
+  c->launches += nl;
+  if (memory == TE_MEM_HOST) {
+    for (int k = 0; k < 3; ++k)
+      if (host_o[k]) TE_CUDA(cudaMemcpyAsync(host_o[k], o[k], out_bytes, cudaMemcpyDeviceToHost, c->stream));
+    TE_CUDA(cudaStreamSynchronize(c->stream));
+  }
+  return TE_OK;
+}
+
+int te_ipc_export(const void* device_ptr, void* handle) {
+  if (!device_ptr || !handle) return fail(TE_ERR_BAD_ARG, "null argument");
+  cudaIpcMemHandle_t h;
+  TE_CUDA(cudaIpcGetMemHandle(&h, const_cast<void*>(device_ptr)));
+  static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  std::memcpy(handle, &h, sizeof(h));
+  return TE_OK;
+}
+
+int te_ipc_open(const void* handle, void** out) {
+  if (!handle || !out) return fail(TE_ERR_BAD_ARG, "null argument");
+  cudaIpcMemHandle_t h;
+  std::memcpy(&h, handle, sizeof(h));
+  TE_CUDA(cudaIpcOpenMemHandle(out, h, cudaIpcMemLazyEnablePeerAccess));
+  return TE_OK;
+}
+
+int te_ipc_close(void* p) {
+  if (!p) return TE_OK;
+  TE_CUDA(cudaIpcCloseMemHandle(p));
+  return TE_OK;
+}
+
+}  // extern "C"

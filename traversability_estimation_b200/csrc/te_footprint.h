@@ -1,0 +1,32 @@
+// te_footprint.h — host interface of the footprint sweep (te_footprint.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <string>
+#include <vector>
+#include "../../include/te_b200.h"
+#include "te_device.cuh"
+
+namespace te {
+
+struct FootprintState {
+  std::string why;
+  bool valid = false;
+  te_geometry key_geo{};
+  te_footprint_params key_par{};
+  void* d_spiral = nullptr;  // packed (di,dj) of the SpiralIterator visit order
+  size_t spiral_cap = 0;
+  int n_spiral = 0;
+  void* d_block = nullptr;   // per-cell predicate bytes for the slab + halo
+  size_t block_cap = 0;
+  void invalidate() { valid = false; }
+  void release();
+};
+
+int footprint_halo(const te_geometry* g, const te_footprint_params* p);
+
+int launch_footprint(FootprintState& st, const SlabView& v, const te_geometry* g, const te_footprint_params* p,
+                     const std::vector<double>& X, const std::vector<double>& Y, const float* trav, const float* slope,
+                     const float* step, const float* elev, float* out, float* slope_fp, float* step_fp, int sms, cudaStream_t s,
+                     int* launches);
+
+}  // namespace te

@@ -1,0 +1,32 @@
+// te_fused.h — host interface of the fused chain stencil (te_fused.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <string>
+#include <vector>
+#include "../../include/te_b200.h"
+#include "te_kernels.h"
+
+namespace te {
+
+struct FusedState {
+  std::string why;        // why the last eligibility check / launch failed
+  bool valid = false;     // tables below match (geometry, params) of `key_*`
+  te_geometry key_geo{};
+  te_chain_params key_par{};
+  int shape_id = -1;
+  void* d_rowmask = nullptr;  // per-row on-circle membership bits
+  void* d_colmask = nullptr;
+  size_t rowmask_cap = 0, colmask_cap = 0;
+  void invalidate() { valid = false; }
+  void release();
+};
+
+// True when the fused stencil has an instantiation for these window shapes (fills the tables).
+bool fused_eligible(FusedState& st, const std::vector<double>& X, const std::vector<double>& Y, const te_geometry* g,
+                    const te_chain_params* p);
+
+// Returns 0 on success.  Cells whose result could not be certified in fp32 are appended to `list`.
+int launch_chain_fused(FusedState& st, const SlabView& v, const ChainDev& p, const float* elev, const ChainOut& o, unsigned* list,
+                       unsigned* count, unsigned cap, int sms, cudaStream_t s);
+
+}  // namespace te
