@@ -1,0 +1,384 @@
+#!/usr/bin/env python
+"""bench.py — Mcells/s of the full filter chain on synthetic elevation (BASELINE.json metric).
+
+    python bench.py --gpus 1 --steps 20 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...      # the CPU restatement of the reference chain (oracle) on host cores
+
+A "step" is one pass of the hot path (elevation -> slope, step, roughness, traversability) over one
+map: at N=1 the 8192 x 8192 map the >=70 %-of-roofline target is quoted on; at N>1 the map grows with
+N (weak scaling): every rank owns an 8192-row x 8192-column slab of an 8192 x 8192*N map and exchanges
+its 4 boundary columns of `elevation` with its neighbours (NCCL send/recv over NVLink) inside the step.
+`--scaling strong` instead tiles the fixed 8192 x 8192 map (BASELINE config 3 verbatim).
+torch is plumbing only (device memory, streams, torch.distributed); every kernel timed here is ours,
+called through the C ABI of libte_b200.so.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "tools")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+
+ALG_BYTES_PER_CELL = 20  # read elevation 4 B + write slope, step, roughness, traversability
+RES = 0.02
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="chain8192", choices=["chain8192", "chain2048", "batched512", "footprint4096"])
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--kernel", default="auto", choices=["auto", "generic", "fused"])
+    ap.add_argument("--holes", type=float, default=0.01, help="fraction of NaN cells (blobs)")
+    ap.add_argument("--rows", type=int, default=0)
+    ap.add_argument("--cols", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+# synthetic terrain, generated on the device as a pure function of GLOBAL cell coordinates so every
+# rank can build its own slab (spectral fBm + mm noise + raised rectangles + flat patches + NaN blobs)
+# ------------------------------------------------------------------------------------------------
+def terrain_torch(torch, rows, col0, ncols, cols_total, seed, holes, device):
+    g = torch.Generator(device="cpu")
+    g.manual_seed(1234 + seed)
+    ncomp = 14
+    wl = 4.0 * (0.5 ** (torch.arange(ncomp, dtype=torch.float64) * (5.0 / (ncomp - 1))))  # 4 m .. 0.125 m
+    ang = torch.rand(ncomp, generator=g, dtype=torch.float64) * (2 * np.pi)
+    ph = torch.rand(ncomp, generator=g, dtype=torch.float64) * (2 * np.pi)
+    amp = 0.05 * wl / wl[0] * 2.2
+    length_x, length_y = rows * RES, cols_total * RES
+    x = (0.5 * length_x - 0.5 * RES) - RES * torch.arange(rows, dtype=torch.float64)
+    y = (0.5 * length_y - 0.5 * RES) - RES * torch.arange(col0, col0 + ncols, dtype=torch.float64)
+    x = x.to(device)
+    y = y.to(device)
+    z = torch.zeros((ncols, rows), dtype=torch.float32, device=device)
+    for k in range(ncomp):
+        kx = float(2 * np.pi / wl[k] * torch.cos(ang[k]))
+        ky = float(2 * np.pi / wl[k] * torch.sin(ang[k]))
+        arg = (ky * y)[:, None] + (kx * x + float(ph[k]))[None, :]
+        z += float(amp[k]) * torch.sin(arg).to(torch.float32)
+    ii = torch.arange(rows, device=device, dtype=torch.int64)[None, :]
+    jj = torch.arange(col0, col0 + ncols, device=device, dtype=torch.int64)[:, None]
+
+    def h32(a, b, salt):
+        h = (a * 73856093) ^ (b * 19349663) ^ (salt * 83492791 + seed * 2654435761)
+        h = (h ^ (h >> 13)) * 1274126177
+        h = h ^ (h >> 16)
+        return h & 0x7FFFFFFF
+
+    z += 1e-3 * ((h32(ii, jj, 1) % 20001).to(torch.float32) / 10000.0 - 1.0)  # +-1 mm sensor-like noise
+    # raised rectangles (cliffs) and exactly flat patches on a 512-cell lattice
+    ci, cj = ii // 512, jj // 512
+    for salt, kind in ((2, "cliff"), (3, "flat")):
+        oi = 32 + h32(ci, cj, salt) % 256
+        oj = 32 + h32(ci, cj, salt + 10) % 256
+        hi = 24 + h32(ci, cj, salt + 20) % 160
+        hj = 24 + h32(ci, cj, salt + 30) % 160
+        li, lj = ii - ci * 512, jj - cj * 512
+        inside = (li >= oi) & (li < oi + hi) & (lj >= oj) & (lj < oj + hj) & (h32(ci, cj, salt + 40) % 4 < 2)
+        if kind == "cliff":
+            z = torch.where(inside, z + 0.2, z)
+        else:
+            z = torch.where(inside, torch.full_like(z, 0.125), z)
+    if holes > 0:
+        # one candidate blob (radius 4 cells, ~50 cells) per 64 x 64 block, kept with probability p
+        p = min(1.0, holes * 4096.0 / 50.0)
+        bi, bj = ii // 64, jj // 64
+        oi = 8 + h32(bi, bj, 5) % 48
+        oj = 8 + h32(bi, bj, 6) % 48
+        keep = (h32(bi, bj, 7) % 10000) < int(p * 10000)
+        li, lj = ii - bi * 64, jj - bj * 64
+        hole = keep & (((li - oi) ** 2 + (lj - oj) ** 2) <= 16)
+        z = torch.where(hole, torch.full_like(z, float("nan")), z)
+    return z.contiguous()
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [t.strip() for t in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def profile_traffic():
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture, if any."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "roofline_latest.json")) as f:
+            return json.load(f)
+    except Exception:
+        return None
+
+
+def run_reference(args):
+    """`--impl reference`: the reference's own CPU algorithm for this path — its restatement in oracle/ (the ROS/Eigen
+    sources cannot be built in this image) — on all host threads; every step is a bounded 2048 x 2048 sample of the map."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import binding as ob
+    import synth
+    n = 2048 if args.rows == 0 else args.rows
+    z = synth.terrain(n, n, RES, seed=3, preset="mixed", holes=args.holes)
+    g = ob.Geometry.make(n, n, RES)
+    p = ob.ChainParams.yaml_defaults(0)
+    threads = ob.max_threads()
+    for _ in range(args.warmup):
+        ob.chain(g, p, z)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ob.chain(g, p, z)
+    dt = time.perf_counter() - t0
+    val = n * n * args.steps / dt / 1e6
+    out = {"impl": "reference", "metric": "Mcells/s full filter chain, synthetic elevation", "value": val, "unit": "Mcells/s",
+           "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+           "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64 compute / f32 layers",
+           "data": "synthetic", "config": {"workload": args.workload, "sample": f"{n}x{n} crop per step", "holes": args.holes},
+           "cpu_baseline": {"value": val, "unit": "Mcells/s", "cores": threads, "kind": "port",
+                            "sample": f"{n}x{n} cells per step, {args.steps} steps, OpenMP over {threads} host threads; "
+                                      "restated CPU chain (not the ROS/Eigen binary)"},
+           "e2e": {"value": val, "unit": "Mcells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out))
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    import traversability_estimation_b200 as te
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    assert world == args.gpus or world == 1, (world, args.gpus)
+
+    rows = args.rows or {"chain8192": 8192, "chain2048": 2048}.get(args.workload, 8192)
+    base_cols = args.cols or rows
+    if args.scaling == "weak":
+        cols_total, my_cols, col0 = base_cols * world, base_cols, base_cols * rank
+    else:
+        assert base_cols % world == 0
+        cols_total, my_cols, col0 = base_cols, base_cols // world, (base_cols // world) * rank
+    H = 4  # dependency radius of the YAML chain at 0.02 m (cells)
+    hl = H if rank > 0 else 0
+    hr = H if rank < world - 1 else 0
+
+    g = te.Geometry.make(rows, cols_total, RES)
+    prm = te.ChainParams.yaml_defaults(0)
+    slab = te.Slab(col0, my_cols, hl, hr)
+    ctx = te.Context(local)
+    ctx.set_kernel({"auto": te.KERNEL_AUTO, "generic": te.KERNEL_GENERIC, "fused": te.KERNEL_FUSED}[args.kernel])
+    stream = torch.cuda.current_stream()
+    ctx.set_stream(stream.cuda_stream)
+
+    own = terrain_torch(torch, rows, col0, my_cols, cols_total, 3, args.holes, dev)  # (my_cols, rows): column-major layer
+    elev = torch.full((hl + my_cols + hr, rows), float("nan"), dtype=torch.float32, device=dev)
+    elev[hl:hl + my_cols].copy_(own)
+    outs = [torch.empty((my_cols, rows), dtype=torch.float32, device=dev) for _ in range(4)]
+
+    def exchange():
+        if world == 1:
+            return
+        ops = []
+        if rank > 0:
+            ops.append(dist.P2POp(dist.isend, elev[hl:hl + H], rank - 1))
+            ops.append(dist.P2POp(dist.irecv, elev[0:hl], rank - 1))
+        if rank < world - 1:
+            ops.append(dist.P2POp(dist.isend, elev[hl + my_cols - H:hl + my_cols], rank + 1))
+            ops.append(dist.P2POp(dist.irecv, elev[hl + my_cols:hl + my_cols + hr], rank + 1))
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+
+    def step():
+        exchange()
+        ctx.chain(g, prm, elev, outs[0], outs[1], outs[2], outs[3], te.MEM_DEVICE, slab=slab)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    ctx.timing()  # drop anything accumulated
+    ctx.enable_timing(True)
+    launches0, _ = ctx.stats()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record(stream)
+    for _ in range(args.steps):
+        step()
+    ev1.record(stream)
+    barrier()
+    ms_total = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if rank == 0 else None
+    main_ms, fix_ms, nlaunch = ctx.timing()
+    ctx.enable_timing(False)
+    launches1, slow_cells = ctx.stats()
+    t = torch.tensor([ms_total, main_ms / max(nlaunch, 1), fix_ms / max(nlaunch, 1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total, main_avg, fix_avg = (float(v) for v in t.tolist())
+    cells_total = rows * cols_total
+    value = cells_total * args.steps / (ms_total * 1e-3) / 1e6
+
+    # ---- end-to-end through the C ABI with HOST (pinned) buffers: H2D + kernels + D2H inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        h_in = torch.empty((hl + my_cols + hr, rows), dtype=torch.float32).pin_memory()
+        h_in.copy_(elev)
+        h_out = [torch.empty((my_cols, rows), dtype=torch.float32).pin_memory() for _ in range(4)]
+        ctx.set_stream(None)
+        nsteps_e2e = max(3, min(args.steps, 10))
+        for _ in range(2):
+            ctx.chain(g, prm, h_in.data_ptr(), *[o.data_ptr() for o in h_out], te.MEM_HOST, slab=slab)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(nsteps_e2e):
+            ctx.chain(g, prm, h_in.data_ptr(), *[o.data_ptr() for o in h_out], te.MEM_HOST, slab=slab)
+        barrier()
+        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        e2e = {"value": cells_total * nsteps_e2e / float(dt) / 1e6, "unit": "Mcells/s",
+               "h2d_bytes_per_step": int(h_in.numel() * 4 * world), "d2h_bytes_per_step": int(4 * my_cols * rows * 4 * world),
+               "steps": nsteps_e2e, "note": "te_chain(TE_MEM_HOST) from pinned host layers; slab + halo taken from the host map"}
+        ctx.set_stream(stream.cuda_stream)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- CPU baseline: the oracle (restated reference chain) on a bounded crop, host threads
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        from oracle import binding as ob
+        n = min(2048, rows, my_cols)
+        crop = np.asfortranarray(own[:n, :n].cpu().numpy().T)
+        og = ob.Geometry.make(n, n, RES)
+        op = ob.ChainParams.yaml_defaults(0)
+        threads = ob.max_threads()
+        ob.chain(og, op, crop[:256, :256].copy(order="F") if n > 256 else crop)  # warm the thread pool
+        t0 = time.perf_counter()
+        ob.chain(og, op, crop)
+        dt = time.perf_counter() - t0
+        cpu = {"value": n * n / dt / 1e6, "unit": "Mcells/s", "cores": threads, "kind": "port",
+               "sample": f"{n}x{n} crop of the same map, one pass, OpenMP over {threads} host threads "
+                         f"({dt:.2f} s); restated CPU chain, not the ROS/Eigen binary"}
+
+    peak, peak_src = measured_peak()
+    cells_per_launch = rows * my_cols
+    achieved = ALG_BYTES_PER_CELL * cells_per_launch / (main_avg * 1e-3) / 1e9 if main_avg > 0 else None
+    prof = profile_traffic()
+    out = {
+        "metric": "Mcells/s full filter chain, synthetic elevation", "value": value, "unit": "Mcells/s",
+        "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps,
+        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32 (f64 certified slow path)",
+        "data": "synthetic",
+        "config": {"workload": f"{rows}x{cols_total} elevation @ {RES} m, full fused chain (YAML parameters), "
+                               f"{world} column slab(s) of {rows}x{my_cols}" + (" + 4-column NCCL halo exchange" if world > 1 else ""),
+                   "holes": args.holes, "kernel": args.kernel,
+                   "l2": "working set 1.34 GB/GPU > 126 MB L2, no flush needed" if rows * my_cols * 20 > 3e8 else "L2-resident",
+                   "slow_path_cells_per_launch": int(slow_cells)},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": (achieved / peak) if achieved else None,
+                     "traffic": (prof or {}).get("dram_bytes_per_launch"), "peak_source": peak_src,
+                     "kernel": "k_chain_fused" if args.kernel != "generic" else "k_chain_generic",
+                     "kernel_ms": main_avg, "fixup_kernel_ms": fix_avg,
+                     "algorithmic_bytes_per_launch": ALG_BYTES_PER_CELL * cells_per_launch},
+        "cpu_baseline": cpu,
+        "e2e": e2e,
+        "gpu_launches": int(launches1 - launches0),
+        "clocks": clocks,
+    }
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -110,6 +110,12 @@ int te_set_kernel(te_ctx* ctx, int te_kernel_choice);
 /* Counters since creation: kernels launched, cells that took the certified slow path in the fused kernel. */
 int te_get_stats(te_ctx* ctx, int64_t* kernel_launches, int64_t* slow_path_cells);
 
+/* Device-side timing of the kernels this context launches (CUDA events on the launching stream).
+ * te_get_timing waits for the stream, returns the accumulated milliseconds of the main chain kernel
+ * and of the fix-up kernel and the number of timed launches, then resets the accumulators. */
+int te_enable_timing(te_ctx* ctx, int on);
+int te_get_timing(te_ctx* ctx, double* main_ms, double* fixup_ms, int64_t* samples);
+
 /* filters::SlopeFilter<grid_map::GridMap>::update — traversability_estimation_filters/src/SlopeFilter.cpp:59-89.
  * in: surface_normal_z, out: the `map_type` layer. */
 int te_slope(te_ctx* ctx, const te_geometry* g, double critical_value, const float* surface_normal_z,

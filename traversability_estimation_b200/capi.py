@@ -14,7 +14,7 @@ MEM_HOST, MEM_DEVICE = 0, 1
 KERNEL_AUTO, KERNEL_GENERIC, KERNEL_FUSED = 0, 1, 2
 
 EXPORTS = ["te_create", "te_destroy", "te_last_error", "te_abi_version", "te_set_stream", "te_synchronize",
-           "te_set_kernel", "te_get_stats", "te_slope", "te_normals", "te_step", "te_roughness", "te_chain",
+           "te_set_kernel", "te_get_stats", "te_enable_timing", "te_get_timing", "te_slope", "te_normals", "te_step", "te_roughness", "te_chain",
            "te_chain_batched", "te_footprint", "te_ipc_export", "te_ipc_open", "te_ipc_close"]
 
 
@@ -99,6 +99,8 @@ def load_library():
         L.te_synchronize.argtypes = [vp]
         L.te_set_kernel.argtypes = [vp, C.c_int]
         L.te_get_stats.argtypes = [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+        L.te_enable_timing.argtypes = [vp, C.c_int]
+        L.te_get_timing.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int64)]
         L.te_slope.argtypes = [vp, G, C.c_double, fp, fp, C.c_int]
         L.te_normals.argtypes = [vp, G, P, fp, fp, fp, fp, C.c_int]
         L.te_step.argtypes = [vp, G, P, fp, fp, C.c_int]
@@ -163,6 +165,15 @@ class Context:
         a, b = C.c_int64(), C.c_int64()
         self._check(self._L.te_get_stats(self._h, C.byref(a), C.byref(b)))
         return a.value, b.value
+
+    def enable_timing(self, on=True):
+        self._check(self._L.te_enable_timing(self._h, 1 if on else 0))
+
+    def timing(self):
+        """(main kernel ms, fix-up kernel ms, timed launches) since the last call."""
+        a, b, n = C.c_double(), C.c_double(), C.c_int64()
+        self._check(self._L.te_get_timing(self._h, C.byref(a), C.byref(b), C.byref(n)))
+        return a.value, b.value, n.value
 
     def slope(self, g, critical, nz, out, memory):
         self._check(self._L.te_slope(self._h, C.byref(g), critical, _addr(nz), _addr(out), memory))

@@ -87,6 +87,10 @@ struct te_ctx {
   DevBuf worklist, counter;  // fused-kernel fix-up list
   te::FusedState fused;      // tensor maps / tables of the fused stencil
   te::FootprintState fp;
+
+  bool timing = false;
+  struct Ev3 { cudaEvent_t a, b, c; };
+  std::vector<Ev3> events;
 };
 
 namespace {
@@ -245,13 +249,23 @@ int run_chain_device(te_ctx* c, const te_geometry* g, const te_slab& s, const te
       if (om.ny) om.ny += m * out_stride;
       if (om.nz) om.nz += m * out_stride;
       TE_CUDA(cudaMemsetAsync(c->counter.p, 0, sizeof(unsigned) * 4, c->stream));
+      te_ctx::Ev3 ev{};
+      if (c->timing) {
+        TE_CUDA(cudaEventCreate(&ev.a)); TE_CUDA(cudaEventCreate(&ev.b)); TE_CUDA(cudaEventCreate(&ev.c));
+        TE_CUDA(cudaEventRecord(ev.a, c->stream));
+      }
       int rc = te::launch_chain_fused(c->fused, v, d, elev + m * in_stride, om, (unsigned*)c->worklist.p,
                                       (unsigned*)c->counter.p, cap, c->sms, c->stream);
       if (rc != 0) return fail(TE_ERR_CUDA, "fused chain launch failed: %s", c->fused.why.c_str());
       if (int r2 = launch_check(c, "k_chain_fused")) return r2;
+      if (c->timing) TE_CUDA(cudaEventRecord(ev.b, c->stream));
       te::launch_fixup(v, d, elev + m * in_stride, om, (const unsigned*)c->worklist.p, (const unsigned*)c->counter.p, cap, c->sms,
                        c->stream);
       if (int r2 = launch_check(c, "k_fixup_cells")) return r2;
+      if (c->timing) {
+        TE_CUDA(cudaEventRecord(ev.c, c->stream));
+        c->events.push_back(ev);
+      }
     }
   } else {
     for (int m = 0; m < nmaps; ++m) {
@@ -260,8 +274,18 @@ int run_chain_device(te_ctx* c, const te_geometry* g, const te_slab& s, const te
       if (om.nx) om.nx += m * out_stride;
       if (om.ny) om.ny += m * out_stride;
       if (om.nz) om.nz += m * out_stride;
+      te_ctx::Ev3 ev{};
+      if (c->timing) {
+        TE_CUDA(cudaEventCreate(&ev.a)); TE_CUDA(cudaEventCreate(&ev.b)); TE_CUDA(cudaEventCreate(&ev.c));
+        TE_CUDA(cudaEventRecord(ev.a, c->stream));
+      }
       te::launch_chain_generic(v, d, elev + m * in_stride, om, c->sms, c->stream);
       if (int r2 = launch_check(c, "k_chain_generic")) return r2;
+      if (c->timing) {
+        TE_CUDA(cudaEventRecord(ev.b, c->stream));
+        TE_CUDA(cudaEventRecord(ev.c, c->stream));
+        c->events.push_back(ev);
+      }
     }
   }
   return TE_OK;
@@ -353,6 +377,31 @@ int te_get_stats(te_ctx* c, int64_t* launches, int64_t* slow) {
     }
     *slow = (int64_t)last[0];
   }
+  return TE_OK;
+}
+
+int te_enable_timing(te_ctx* c, int on) {
+  TE_ENTER(c);
+  c->timing = on != 0;
+  return TE_OK;
+}
+
+int te_get_timing(te_ctx* c, double* main_ms, double* fixup_ms, int64_t* samples) {
+  TE_ENTER(c);
+  TE_CUDA(cudaStreamSynchronize(c->stream));
+  double m = 0.0, f = 0.0;
+  for (auto& e : c->events) {
+    float t1 = 0.f, t2 = 0.f;
+    TE_CUDA(cudaEventElapsedTime(&t1, e.a, e.b));
+    TE_CUDA(cudaEventElapsedTime(&t2, e.b, e.c));
+    m += t1;
+    f += t2;
+    cudaEventDestroy(e.a); cudaEventDestroy(e.b); cudaEventDestroy(e.c);
+  }
+  if (main_ms) *main_ms = m;
+  if (fixup_ms) *fixup_ms = f;
+  if (samples) *samples = (int64_t)c->events.size();
+  c->events.clear();
   return TE_OK;
 }
 

@@ -287,33 +287,38 @@ __device__ __forceinline__ ElevAccess make_access(const SlabView& v, const float
   return ElevAccess{e, v.rows, v.in_col0, v.in_ncols, v.cols_total};
 }
 
-// One cell of the whole chain.  `mask` selects the outputs to produce (bit 0 normals/slope/
-// roughness/fuse, bit 1 step) so that the fix-up pass can leave the exact step layer alone.
+// One cell of the whole chain.  The fix-up pass of the fused stencil recomputes only the part it
+// could not certify (normals/slope/roughness and/or step) and always re-fuses.
 __device__ void chain_cell_literal(const SlabView& v, const ChainDev& p, const float* elev, int i, int j,
-                                   ChainOut o, bool redo_step) {
+                                   ChainOut o, bool do_normals, bool do_step) {
   const ElevAccess E = make_access(v, elev);
   const size_t oc = (size_t)(j - v.out_col0) * v.rows + i;
-  float fnx = nanf_(), fny = nanf_(), fnz = nanf_();
-  if (finitef(E(i, j))) {
-    double n[3];
-    normal_literal(v, p, E, i, j, n);
-    fnx = (float)n[0]; fny = (float)n[1]; fnz = (float)n[2];
+  float s, r, t;
+  if (do_normals) {
+    float fnx = nanf_(), fny = nanf_(), fnz = nanf_();
+    if (finitef(E(i, j))) {
+      double n[3];
+      normal_literal(v, p, E, i, j, n);
+      fnx = (float)n[0]; fny = (float)n[1]; fnz = (float)n[2];
+    }
+    s = slope_literal(fnz, p.slope_crit);
+    r = roughness_literal(v, p, E, i, j, fnx, fny, fnz);
+    o.slope[oc] = s;
+    o.rough[oc] = r;
+    if (o.nx) o.nx[oc] = fnx;
+    if (o.ny) o.ny[oc] = fny;
+    if (o.nz) o.nz[oc] = fnz;
+  } else {
+    s = o.slope[oc];
+    r = o.rough[oc];
   }
-  const float s = slope_literal(fnz, p.slope_crit);
-  const float r = roughness_literal(v, p, E, i, j, fnx, fny, fnz);
-  float t;
-  if (redo_step) {
+  if (do_step) {
     t = step_literal(v, p, E, i, j);
     o.step[oc] = t;
   } else {
     t = o.step[oc];
   }
-  o.slope[oc] = s;
-  o.rough[oc] = r;
   o.trav[oc] = __fmul_rn(p.fuse_w, __fadd_rn(__fadd_rn(s, t), r));
-  if (o.nx) o.nx[oc] = fnx;
-  if (o.ny) o.ny[oc] = fny;
-  if (o.nz) o.nz[oc] = fnz;
 }
 
 __global__ void __launch_bounds__(128) k_chain_generic(SlabView v, ChainDev p, const float* __restrict__ elev, ChainOut o) {
@@ -321,21 +326,22 @@ __global__ void __launch_bounds__(128) k_chain_generic(SlabView v, ChainDev p, c
   for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < total; c += (long long)gridDim.x * blockDim.x) {
     const int i = (int)(c % v.rows);
     const int j = v.out_col0 + (int)(c / v.rows);
-    chain_cell_literal(v, p, elev, i, j, o, true);
+    chain_cell_literal(v, p, elev, i, j, o, true, true);
   }
 }
 
-// Certified slow path of the fused stencil: recompute the listed cells (packed as j_local*rows+i).
+// Certified slow path of the fused stencil: recompute the listed cells (j_local*rows+i | flags<<30).
 __global__ void __launch_bounds__(128) k_fixup_cells(SlabView v, ChainDev p, const float* __restrict__ elev, ChainOut o,
                                                      const unsigned int* __restrict__ list,
                                                      const unsigned int* __restrict__ count, unsigned int cap) {
   unsigned int n = *count;
   if (n > cap) n = cap;
   for (unsigned int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
-    const unsigned int c = list[k];
+    const unsigned int w = list[k];
+    const unsigned int c = w & 0x3fffffffu;  // bit 30: normals part, bit 31: step part
     const int i = (int)(c % (unsigned)v.rows);
     const int j = v.out_col0 + (int)(c / (unsigned)v.rows);
-    chain_cell_literal(v, p, elev, i, j, o, false);
+    chain_cell_literal(v, p, elev, i, j, o, (w >> 30) & 1u, (w >> 31) & 1u);
   }
 }
 
