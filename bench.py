@@ -247,7 +247,8 @@ def main():
     slab = te.Slab(col0, my_cols, hl, hr)
     ctx = te.Context(local)
     ctx.set_kernel({"auto": te.KERNEL_AUTO, "generic": te.KERNEL_GENERIC, "fused": te.KERNEL_FUSED}[args.kernel])
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream()  # a real stream: handle 0 (legacy default) would mean "the context's own stream"
+    torch.cuda.set_stream(stream)
     ctx.set_stream(stream.cuda_stream)
 
     own = terrain_torch(torch, rows, col0, my_cols, cols_total, 3, args.holes, dev)  # (my_cols, rows): column-major layer
@@ -342,7 +343,7 @@ def main():
         og = ob.Geometry.make(n, n, RES)
         op = ob.ChainParams.yaml_defaults(0)
         threads = ob.max_threads()
-        ob.chain(og, op, crop[:256, :256].copy(order="F") if n > 256 else crop)  # warm the thread pool
+        ob.chain(ob.Geometry.make(128, 128, RES), op, np.asfortranarray(crop[:128, :128]))  # warm the thread pool
         t0 = time.perf_counter()
         ob.chain(og, op, crop)
         dt = time.perf_counter() - t0

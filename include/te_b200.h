@@ -115,6 +115,10 @@ int te_get_stats(te_ctx* ctx, int64_t* kernel_launches, int64_t* slow_path_cells
  * and of the fix-up kernel and the number of timed launches, then resets the accumulators. */
 int te_enable_timing(te_ctx* ctx, int on);
 int te_get_timing(te_ctx* ctx, double* main_ms, double* fixup_ms, int64_t* samples);
+/* Work-list counters of the last fused launch: [0] cells the fp32 stencil could not certify (tier 2,
+ * fp64 on centred coordinates); [4] cells tier 2 passed on to the literal kernel (tier 3); [1..3] only
+ * when TE_FUSED_STATS is set: cells flagged for eigenvalue cancellation, conditioning, n_z rounding. */
+int te_get_flag_counters(te_ctx* ctx, uint32_t out[5]);
 
 /* filters::SlopeFilter<grid_map::GridMap>::update — traversability_estimation_filters/src/SlopeFilter.cpp:59-89.
  * in: surface_normal_z, out: the `map_type` layer. */

@@ -1,0 +1,23 @@
+"""Calibration run: flagged-cell causes and fp32 error vs certification constants (dev tool, GPU)."""
+import os, sys, json
+sys.path.insert(0, '/root/repo'); sys.path.insert(0, '/root/repo/tools'); sys.path.insert(0, '/root/repo/tests')
+import numpy as np, synth, torch, bench
+import traversability_estimation_b200 as te
+from oracle import binding as ob
+from helpers import compare_layer
+os.environ['TE_FUSED_STATS'] = '1'
+rows = cols = 1024
+dev = torch.device('cuda', 0)
+z_t = bench.terrain_torch(torch, rows, 0, cols, cols, 3, 0.0, dev)
+z = np.asfortranarray(z_t.cpu().numpy().T)
+og = ob.Geometry.make(rows, cols, 0.02); g = te.Geometry.make(rows, cols, 0.02)
+ref = ob.chain(og, ob.ChainParams.yaml_defaults(0), z)
+for rk, ck in [(0.2, 0.25), (0.1, 0.25), (0.05, 0.25), (0.0, 0.25), (0.1, 0.1), (0.1, 0.0), (0.05, 0.1)]:
+    os.environ['TE_FUSED_ROUGH_K'] = str(rk); os.environ['TE_FUSED_COND_K'] = str(ck)
+    ctx = te.Context(0); ctx.set_kernel(te.KERNEL_FUSED)
+    got = ctx.chain_host(g, te.ChainParams.yaml_defaults(0), z)
+    cnt = ctx.flag_counters()
+    rep = {k: compare_layer(got[k], ref[k], k) for k in ('slope', 'roughness', 'traversability')}
+    print(f"rough_k={rk} cond_k={ck} flagged={cnt} frac={cnt[0]/rows/cols:.4f}  " +
+          "  ".join(f"{k}: oot={r['out_of_tol']} max={r['max_abs']:.2e}" for k, r in rep.items()))
+    ctx.close()

@@ -11,8 +11,8 @@ for (rows, cols, seed, preset, res) in [(128, 96, 1, 'gentle', 0.02), (256, 200,
     ref = ob.chain(og, ob.ChainParams.yaml_defaults(0), z, with_normals=True)
     ctx.set_kernel(te.KERNEL_FUSED)
     got = ctx.chain_host(g, te.ChainParams.yaml_defaults(0), z, with_normals=True)
-    l, slow = ctx.stats()
-    print(rows, cols, preset, res, 'slow cells', slow, 'of', rows*cols)
+    cnt = ctx.flag_counters()
+    print(rows, cols, preset, res, 'tier2 cells', cnt[0], 'tier3 cells', cnt[4], 'of', rows*cols)
     for k in ('slope','step','roughness','traversability','nx','ny','nz'):
         r = compare_layer(got[k], ref[k], k)
         print('   ', {kk: r[kk] for kk in ('name','nan_mismatch','out_of_tol','rel_only_violations','branch_mismatch','bit_exact','max_abs')})

@@ -14,7 +14,7 @@ MEM_HOST, MEM_DEVICE = 0, 1
 KERNEL_AUTO, KERNEL_GENERIC, KERNEL_FUSED = 0, 1, 2
 
 EXPORTS = ["te_create", "te_destroy", "te_last_error", "te_abi_version", "te_set_stream", "te_synchronize",
-           "te_set_kernel", "te_get_stats", "te_enable_timing", "te_get_timing", "te_slope", "te_normals", "te_step", "te_roughness", "te_chain",
+           "te_set_kernel", "te_get_stats", "te_enable_timing", "te_get_timing", "te_get_flag_counters", "te_slope", "te_normals", "te_step", "te_roughness", "te_chain",
            "te_chain_batched", "te_footprint", "te_ipc_export", "te_ipc_open", "te_ipc_close"]
 
 
@@ -174,6 +174,12 @@ class Context:
         a, b, n = C.c_double(), C.c_double(), C.c_int64()
         self._check(self._L.te_get_timing(self._h, C.byref(a), C.byref(b), C.byref(n)))
         return a.value, b.value, n.value
+
+    def flag_counters(self):
+        a = (C.c_uint32 * 5)()
+        self._L.te_get_flag_counters.argtypes = [C.c_void_p, C.POINTER(C.c_uint32)]
+        self._check(self._L.te_get_flag_counters(self._h, a))
+        return list(a)
 
     def slope(self, g, critical, nz, out, memory):
         self._check(self._L.te_slope(self._h, C.byref(g), critical, _addr(nz), _addr(out), memory))

@@ -84,7 +84,7 @@ struct te_ctx {
   std::vector<double> hX, hY;
 
   DevBuf stage[12];          // TE_MEM_HOST staging: 0..3 inputs, 4..11 outputs
-  DevBuf worklist, counter;  // fused-kernel fix-up list
+  DevBuf worklist, worklist3, counter;  // fused-kernel fix-up lists (tier 2, tier 3) and their counters
   te::FusedState fused;      // tensor maps / tables of the fused stencil
   te::FootprintState fp;
 
@@ -241,14 +241,15 @@ int run_chain_device(te_ctx* c, const te_geometry* g, const te_slab& s, const te
   if (use_fused) {
     const unsigned cap = (unsigned)std::min<size_t>(out_stride, (size_t)1 << 26);
     TE_CUDA(c->worklist.reserve(sizeof(unsigned) * (size_t)cap));
-    TE_CUDA(c->counter.reserve(sizeof(unsigned) * 4));
+    TE_CUDA(c->worklist3.reserve(sizeof(unsigned) * (size_t)cap));
+    TE_CUDA(c->counter.reserve(sizeof(unsigned) * 8));
     for (int m = 0; m < nmaps; ++m) {
       te::ChainOut om = o;
       om.slope += m * out_stride; om.step += m * out_stride; om.rough += m * out_stride; om.trav += m * out_stride;
       if (om.nx) om.nx += m * out_stride;
       if (om.ny) om.ny += m * out_stride;
       if (om.nz) om.nz += m * out_stride;
-      TE_CUDA(cudaMemsetAsync(c->counter.p, 0, sizeof(unsigned) * 4, c->stream));
+      TE_CUDA(cudaMemsetAsync(c->counter.p, 0, sizeof(unsigned) * 8, c->stream));
       te_ctx::Ev3 ev{};
       if (c->timing) {
         TE_CUDA(cudaEventCreate(&ev.a)); TE_CUDA(cudaEventCreate(&ev.b)); TE_CUDA(cudaEventCreate(&ev.c));
@@ -259,7 +260,12 @@ int run_chain_device(te_ctx* c, const te_geometry* g, const te_slab& s, const te
       if (rc != 0) return fail(TE_ERR_CUDA, "fused chain launch failed: %s", c->fused.why.c_str());
       if (int r2 = launch_check(c, "k_chain_fused")) return r2;
       if (c->timing) TE_CUDA(cudaEventRecord(ev.b, c->stream));
-      te::launch_fixup(v, d, elev + m * in_stride, om, (const unsigned*)c->worklist.p, (const unsigned*)c->counter.p, cap, c->sms,
+      te::FixupArgs fa;
+      te::make_fixup_args(c->fused, v, d, &fa);
+      te::launch_fixup_t2(fa, elev + m * in_stride, om, (const unsigned*)c->worklist.p, (const unsigned*)c->counter.p, cap,
+                          (unsigned*)c->worklist3.p, (unsigned*)c->counter.p + 4, c->sms, c->stream);
+      if (int r2 = launch_check(c, "k_fixup_t2")) return r2;
+      te::launch_fixup(v, d, elev + m * in_stride, om, (const unsigned*)c->worklist3.p, (const unsigned*)c->counter.p + 4, cap, c->sms,
                        c->stream);
       if (int r2 = launch_check(c, "k_fixup_cells")) return r2;
       if (c->timing) {
@@ -336,6 +342,7 @@ int te_destroy(te_ctx* c) {
       c->dY.release();
       for (auto& b : c->stage) b.release();
       c->worklist.release();
+      c->worklist3.release();
       c->counter.release();
       c->fused.release();
       c->fp.release();
@@ -402,6 +409,17 @@ int te_get_timing(te_ctx* c, double* main_ms, double* fixup_ms, int64_t* samples
   if (fixup_ms) *fixup_ms = f;
   if (samples) *samples = (int64_t)c->events.size();
   c->events.clear();
+  return TE_OK;
+}
+
+int te_get_flag_counters(te_ctx* c, uint32_t out[5]) {
+  TE_ENTER(c);
+  if (!out) return fail(TE_ERR_BAD_ARG, "null argument");
+  for (int k = 0; k < 5; ++k) out[k] = 0;
+  if (c->counter.p) {
+    TE_CUDA(cudaStreamSynchronize(c->stream));
+    TE_CUDA(cudaMemcpy(out, c->counter.p, 20, cudaMemcpyDeviceToHost));
+  }
   return TE_OK;
 }
 

@@ -1,0 +1,240 @@
+// te_fixup.cu — second tier of the fused stencil's certification ladder.
+//
+// Tier 1 (te_fused.cu) is fp32 with a closed form that assumes a full, valid disk window.  Cells it
+// cannot certify land on a work list.  This tier recomputes them in fp64 on window-centred
+// coordinates with validity-aware moments (map borders, NaN holes), which is accurate to ~1e-13 —
+// far inside one float32 ulp — and escalates to tier 3 (the literal kernel in te_generic.cu, which
+// replays the reference's own operand order on absolute coordinates) only where even that cannot
+// decide: numerically rank-deficient scatter matrices (the reference's FullPivHouseholderQR rank
+// test), ill-conditioned eigenvectors, or n_z within 1e-9 of a float32 rounding boundary.
+#include "te_fused.h"
+
+namespace te {
+namespace {
+
+struct Elev {
+  const float* __restrict__ e;
+  int rows, col0, ncols, cols_total;
+  __device__ __forceinline__ float operator()(int a, int b) const {
+    if (a < 0 || a >= rows || b < 0 || b >= cols_total) return nanf_();
+    const int lb = b - col0;
+    if (lb < 0 || lb >= ncols) return nanf_();
+    const float v = __ldg(e + (size_t)lb * rows + a);
+    return finitef(v) ? v : nanf_();
+  }
+};
+
+// step_height of cell (a,b): pass 1 of StepFilter.cpp:112-144 with the integer window description.
+__device__ float step_height_t2(const FixupArgs& A, const Elev& E, int a, int b) {
+  const float zc = E(a, b);
+  if (!finitef(zc)) return nanf_();
+  const unsigned rm = A.rowmask ? A.rowmask[a] : 0u, cm = A.colmask ? A.colmask[b] : 0u;
+  float mn = zc, mx = zc;
+#pragma unroll
+  for (int l = -2; l <= 2; ++l) {
+    const int w = A.w1[l < 0 ? -l : l];
+    for (int k = -w; k <= w; ++k) {
+      const float z = E(a + k, b + l);
+      if (finitef(z)) { mn = fminf(mn, z); mx = fmaxf(mx, z); }
+    }
+  }
+  if (A.tip1) {
+    const float t0 = (rm & 1u) ? E(a - 2, b) : nanf_(), t1 = (rm & 2u) ? E(a + 2, b) : nanf_();
+    const float t2 = (cm & 1u) ? E(a, b - 2) : nanf_(), t3 = (cm & 2u) ? E(a, b + 2) : nanf_();
+    mn = fminf(fminf(mn, t0), fminf(t1, fminf(t2, t3)));  // fminf/fmaxf skip NaN operands
+    mx = fmaxf(fmaxf(mx, t0), fmaxf(t1, fmaxf(t2, t3)));
+  }
+  return (float)((double)mx - (double)mn);
+}
+
+// pass 2 of StepFilter.cpp:147-178
+__device__ float step_t2(const FixupArgs& A, const Elev& E, int i, int j) {
+  const unsigned rm = A.rowmask ? A.rowmask[i] : 0u, cm = A.colmask ? A.colmask[j] : 0u;
+  double stepMax = 0.0;
+  int n = 0;
+  bool any = false;
+  auto visit = [&](int a, int b) {
+    const float sh = step_height_t2(A, E, a, b);
+    if (!finitef(sh)) return;
+    any = true;
+    if ((double)sh > stepMax) stepMax = (double)sh;
+    if ((double)sh > A.step_crit) ++n;
+  };
+  for (int l = -2; l <= 2; ++l) {
+    const int w = A.w2[l < 0 ? -l : l];
+    for (int k = -w; k <= w; ++k) visit(i + k, j + l);
+  }
+  if (A.tip2) {
+    if (rm & 4u) visit(i - 2, j);
+    if (rm & 8u) visit(i + 2, j);
+    if (cm & 4u) visit(i, j - 2);
+    if (cm & 8u) visit(i, j + 2);
+  }
+  if (!any) return nanf_();
+  const double step = fmin(stepMax, (double)n / (double)A.ncrit * stepMax);
+  return (float)(step < A.step_crit ? 1.0 - step / A.step_crit : 0.0);
+}
+
+// Normals + slope + roughness of one cell in fp64 on centred coordinates.  Returns false when the
+// result cannot be certified at this tier.
+__device__ bool normals_t2(const FixupArgs& A, const Elev& E, int i, int j, float& fnx, float& fny, float& fnz, float& slope,
+                           float& rough) {
+  const float zc = E(i, j);
+  if (!finitef(zc)) {  // hole: no normal, slope and roughness stay NaN (SlopeFilter.cpp:71, RoughnessFilter.cpp:84)
+    fnx = fny = fnz = slope = rough = nanf_();
+    return true;
+  }
+  double n = 0, su = 0, sv = 0, sw = 0, suu = 0, suv = 0, svv = 0, suw = 0, svw = 0, sww = 0;
+#pragma unroll
+  for (int l = -2; l <= 2; ++l) {
+    const int w = A.wn[l < 0 ? -l : l];
+    for (int k = -w; k <= w; ++k) {
+      const float z = E(i + k, j + l);
+      if (!finitef(z)) continue;
+      const double u = -A.res * (double)k, v = -A.res * (double)l, d = (double)z - (double)zc;
+      n += 1.0; su += u; sv += v; sw += d;
+      suu += u * u; suv += u * v; svv += v * v; suw += u * d; svw += v * d; sww += d * d;
+    }
+  }
+  double nx = 0.0, ny = 0.0, nz = 1.0;
+  const double mu = su / n, mv = sv / n, mw = sw / n;
+  // scatter matrix sum (p - mean)(p - mean)^T
+  const double xx = suu - su * mu, xy = suv - su * mv, xz = suw - su * mw;
+  const double yy = svv - sv * mv, yz = svw - sv * mw, zz = sww - sw * mw;
+  if (n >= 3.0 && zz > 0.0) {
+    double bx, by, bz;
+    if (n == A.n_full) {
+      // full disk window: scatter = [[a,0,p],[0,a,q],[p,q,c]] (sums of u, v, uv vanish by symmetry) and
+      // the eigen-problem collapses to 2x2 — robust even when two eigenvalues nearly coincide
+      const double a = 0.5 * (xx + yy), g2 = xz * xz + yz * yz;
+      const double h = 0.5 * (a - zz), D = sqrt(h * h + g2);
+      const double dph = D + fabs(h);
+      if (!(dph > 0.0)) return false;
+      const double qq = g2 / dph;
+      const double m = h >= 0.0 ? dph : qq;           // a - lambda0
+      const double lam = (h >= 0.0 ? zz : a) - qq;     // lambda0
+      const double big = fmax(a, zz);
+      if (!(lam > 1e-9 * big)) return false;           // rank: the literal QR decides (tier 3)
+      if (!(fmin(2.0 * D, m) > 1e-7 * big)) return false;
+      bx = -xz; by = -yz; bz = m;
+    } else {
+      const double c2 = xx + yy + zz;
+      const double c1 = xx * yy + xx * zz + yy * zz - xy * xy - xz * xz - yz * yz;
+      const double c0 = xx * (yy * zz - yz * yz) - xy * (xy * zz - yz * xz) + xz * (xy * yz - yy * xz);
+      double lam = 0.0, dp = -c1;
+      bool conv = false;
+#pragma unroll 1
+      for (int it = 0; it < 40; ++it) {  // Newton from below: monotone convergence to the smallest root
+        const double p = ((-lam + c2) * lam - c1) * lam + c0;
+        dp = (-3.0 * lam + 2.0 * c2) * lam - c1;
+        if (dp == 0.0) break;
+        const double step = p / dp;
+        lam -= step;
+        if (fabs(step) <= 1e-15 * c2) { conv = true; break; }
+      }
+      dp = (-3.0 * lam + 2.0 * c2) * lam - c1;
+      // rank: lambda0 at the reference's rank-threshold scale -> the literal QR decides (tier 3);
+      // conditioning: |p'(lambda0)| = (l1 - l0)(l2 - l0) must leave the cross products accurate
+      if (!conv || !(lam > 1e-9 * c2) || !(fabs(dp) > 1e-4 * c2 * c2)) return false;
+      const double ax = xx - lam, ay = yy - lam, az = zz - lam;
+      // eigenvector = largest cross product of two rows of (S - lambda0 I)
+      const double v0x = xy * yz - xz * ay, v0y = xz * xy - ax * yz, v0z = ax * ay - xy * xy;  // r0 x r1
+      const double v1x = xy * az - xz * yz, v1y = xz * xz - ax * az, v1z = ax * yz - xy * xz;  // r0 x r2
+      const double v2x = ay * az - yz * yz, v2y = yz * xz - xy * az, v2z = xy * yz - ay * xz;  // r1 x r2
+      const double q0 = v0x * v0x + v0y * v0y + v0z * v0z, q1 = v1x * v1x + v1y * v1y + v1z * v1z, q2 = v2x * v2x + v2y * v2y + v2z * v2z;
+      bx = v0x; by = v0y; bz = v0z;
+      double bq = q0;
+      if (q1 > bq) { bx = v1x; by = v1y; bz = v1z; bq = q1; }
+      if (q2 > bq) { bx = v2x; by = v2y; bz = v2z; bq = q2; }
+    }
+    const double bq = bx * bx + by * by + bz * bz;
+    if (!(bq > 0.0)) return false;
+    const double inv = 1.0 / sqrt(bq);
+    nx = bx * inv; ny = by * inv; nz = bz * inv;
+    if (nz < 0.0) { nx = -nx; ny = -ny; nz = -nz; }
+    if (nz == 0.0) return false;
+    // float32 rounding of n_z: where acos amplifies one ulp beyond the tolerance (theta < ~0.02 rad) the
+    // rounding must be certain: escalate when n_z is within 1e-4 ulp of a rounding boundary (tier-2 error ~2e-6 ulp)
+    if (nz > 0.9998) {
+      const float f = (float)nz;
+      const float up = __uint_as_float(__float_as_uint(f) + 1u), dn = __uint_as_float(__float_as_uint(f) - 1u);
+      const double bu = 0.5 * ((double)f + (double)up), bd = 0.5 * ((double)f + (double)dn);
+      const double guard = 1e-4 * (bu - bd);
+      if (fabs(nz - bu) < guard || fabs(nz - bd) < guard) return false;
+    }
+  } else if (n >= 3.0) {
+    // exactly flat window: scatter has an exact zero row -> rank 2 -> (0,0,1) in the reference too
+  }
+  fnx = (float)nx; fny = (float)ny; fnz = (float)nz;
+  const double th = acos((double)fnz);
+  slope = (float)(th < A.slope_crit ? 1.0 - th / A.slope_crit : 0.0);
+  // roughness with the float32 normal (RoughnessFilter.cpp:108-117)
+  const double NX = fnx, NY = fny, NZ = fnz;
+  double sum = 0.0, cnt = 0.0;
+  const double plane = mu * NX + mv * NY + mw * NZ;
+#pragma unroll
+  for (int l = -2; l <= 2; ++l) {
+    const int w = A.wn[l < 0 ? -l : l];
+    for (int k = -w; k <= w; ++k) {
+      const float z = E(i + k, j + l);
+      if (!finitef(z)) continue;
+      const double d = NX * (-A.res * (double)k) + NY * (-A.res * (double)l) + NZ * ((double)z - (double)zc) - plane;
+      sum += d * d;
+      cnt += 1.0;
+    }
+  }
+  const double r = sqrt(sum / (cnt - 1.0));  // one point: 0/0 = NaN -> comparison false -> 0.0
+  rough = (float)(r < A.rough_crit ? 1.0 - r / A.rough_crit : 0.0);
+  return true;
+}
+
+__global__ void __launch_bounds__(128) k_fixup_t2(FixupArgs A, const float* __restrict__ elev, ChainOut o,
+                                                  const unsigned* __restrict__ list, const unsigned* __restrict__ count,
+                                                  unsigned cap, unsigned* list3, unsigned* count3) {
+  unsigned n = *count;
+  if (n > cap) n = cap;
+  const Elev E{elev, A.rows, A.in_col0, A.in_ncols, A.cols_total};
+  for (unsigned k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+    const unsigned w = list[k];
+    const unsigned c = w & 0x3fffffffu;
+    const int i = (int)(c % (unsigned)A.rows);
+    const int j = A.out_col0 + (int)(c / (unsigned)A.rows);
+    const bool do_n = (w >> 30) & 1u, do_s = (w >> 31) & 1u;
+    float s, r, t;
+    bool escalate = false;
+    if (do_n) {
+      float fx, fy, fz;
+      if (normals_t2(A, E, i, j, fx, fy, fz, s, r)) {
+        o.slope[c] = s;
+        o.rough[c] = r;
+        if (o.nx) { o.nx[c] = fx; o.ny[c] = fy; o.nz[c] = fz; }
+      } else {
+        escalate = true;
+      }
+    } else {
+      s = o.slope[c];
+      r = o.rough[c];
+    }
+    if (do_s) {
+      t = step_t2(A, E, i, j);
+      o.step[c] = t;
+    } else {
+      t = o.step[c];
+    }
+    if (escalate) {
+      const unsigned idx = atomicAdd(count3, 1u);
+      if (idx < cap) list3[idx] = c | (1u << 30);  // tier 3 redoes the normals part and re-fuses
+    } else {
+      o.trav[c] = __fmul_rn(A.fuse_w, __fadd_rn(__fadd_rn(s, t), r));
+    }
+  }
+}
+
+}  // namespace
+
+void launch_fixup_t2(const FixupArgs& a, const float* elev, const ChainOut& o, const unsigned* list, const unsigned* count,
+                     unsigned cap, unsigned* list3, unsigned* count3, int sms, cudaStream_t s) {
+  k_fixup_t2<<<sms * 8, 128, 0, s>>>(a, elev, o, list, count, cap, list3, count3);
+}
+
+}  // namespace te

@@ -27,6 +27,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "te_fused.h"
@@ -34,29 +35,41 @@
 namespace te {
 namespace {
 
-constexpr int STRIP = 64;          // rows per warp strip
-constexpr int EROWS = STRIP + 8;   // staged elevation rows (halo 4 each side)
+constexpr int SROWS = 64;          // rows a warp holds (two adjacent rows per lane): step_height rows
+constexpr int OROWS = 60;          // rows a warp produces (lanes 1..30); pitch of the strips
+constexpr int EROWS = SROWS + 4;   // staged elevation rows (2 more each side for the step_height rows)
 constexpr int CH = 5;              // columns per TMA chunk = unroll factor = ring depth
 constexpr int NST = 4;             // TMA ring stages per warp
-constexpr int STAGE_FLOATS = 384;  // EROWS*CH = 360 floats, padded so every stage is 128-byte aligned
-constexpr int SHROWS = STRIP + 4;  // step_height rows exchanged per column (halo 2)
-constexpr int SHBUF_FLOATS = 80;   // SHROWS padded
-constexpr int WARP_SMEM_BYTES = NST * STAGE_FLOATS * 4 + 2 * SHBUF_FLOATS * 4 + 128;  // 6912
-constexpr int WARPS_PER_CTA = 12;
+constexpr int STAGE_BYTES = 1408;  // EROWS*CH*4 = 1360, padded so every stage is 128-byte aligned
+constexpr int SHBUF_BYTES = 288;   // 2 pad + 64 + 2 pad floats, padded
+constexpr int WARP_SMEM_BYTES = NST * STAGE_BYTES + 2 * SHBUF_BYTES + 64;  // 6272 = 49 * 128
+#ifndef TE_WPC
+#define TE_WPC 12
+#endif
+constexpr int WARPS_PER_CTA = TE_WPC;
 constexpr unsigned FULL = 0xffffffffu;
+
+typedef unsigned long long f2;  // two packed floats in one aligned register pair (see below)
 
 struct FusedArgs {
   int rows, cols_total;
   int in_col0, in_ncols, out_col0, out_ncols;
   int nstrips, nseg, seg_len;
-  float a_cov;      // res^2 * K2 / N   (Cxx = Cyy of a full window)
+  float half_a;     // 0.5 * res^2 * K2 / N   (Cxx = Cyy of a full window is a = 2*half_a)
+  float a_cov;
   float kp;         // -res / N         (Cxz = kp * sum k*w)
   float invN;       // 1 / N
   float n_over_nm1; // N / (N-1)
+  float rough_thr;  // (0.2 / crit_rough)^2 * (N-1)/N : lambda0 below rough_thr*cmag^2 cannot be certified
   float slope_crit, inv_slope_crit;
   float step_crit, inv_step_crit, inv_ncrit;
   float rough_crit, inv_rough_crit;
   float fuse_w;
+  float cond_k;     // eigen-gap / scale ratio below which the fp32 eigenvector is not trusted
+  int stats;        // 1: count[1..3] += cells flagged per cause (lambda0, conditioning, small-angle rounding)
+  // constants pre-broadcast to both halves of a register pair (one LDC.64 each)
+  f2 k_invN, k_minvN, k_kp, k_half_a, k_nnm1, k_rough_thr, k_minv_slope, k_minv_rough, k_m0, k_m1;
+  f2 k_one, k_mone, k_two, k_half, k_mhalf, k_1p5, k_0375, k_m03125, k_p0, k_p1, k_p2, k_p3, k_p4;
   const unsigned char* rowmask;  // per global row: bit0/1 pass-1 tips (-2,0)/(+2,0); bit2/3 pass-2 tips
   const unsigned char* colmask;  // per global column, same bits for (0,-2)/(0,+2)
   float* slope;
@@ -74,57 +87,93 @@ struct FusedArgs {
 // ---------------------------------------------------------------------------------------------
 // packed f32x2 arithmetic (Blackwell FFMA2/FADD2/FMUL2): .x = row i, .y = row i+1 of the lane
 // ---------------------------------------------------------------------------------------------
-struct f2 {
-  float x, y;
-};
-__device__ __forceinline__ unsigned long long pk(f2 a) {
-  unsigned long long r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a.x), "f"(a.y));
+// An f2 lives in ONE aligned 64-bit register pair for its whole life, so FFMA2/FADD2/FMUL2 take it
+// without any repacking; lo()/hi() only name the halves.
+__device__ __forceinline__ f2 mk(float x, float y) {
+  f2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(x), "f"(y));
   return r;
 }
-__device__ __forceinline__ f2 up(unsigned long long v) {
-  f2 r;
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
-  return r;
+__device__ __forceinline__ float lo(f2 v) {
+  float a, b;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+  return a;
+}
+__device__ __forceinline__ float hi(f2 v) {
+  float a, b;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+  return b;
 }
 __device__ __forceinline__ f2 add2(f2 a, f2 b) {
-  unsigned long long r;
-  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(pk(a)), "l"(pk(b)));
-  return up(r);
+  f2 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
 }
 __device__ __forceinline__ f2 sub2(f2 a, f2 b) {
-  unsigned long long r;
-  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(pk(a)), "l"(pk(b)));
-  return up(r);
+  f2 r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
 }
 __device__ __forceinline__ f2 mul2(f2 a, f2 b) {
-  unsigned long long r;
-  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(pk(a)), "l"(pk(b)));
-  return up(r);
+  f2 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
 }
 __device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) {
-  unsigned long long r;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(pk(a)), "l"(pk(b)), "l"(pk(c)));
-  return up(r);
+  f2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
 }
-__device__ __forceinline__ f2 bc(float v) { return f2{v, v}; }
+__device__ __forceinline__ f2 bc(float v) { return mk(v, v); }
+__device__ __forceinline__ f2 neg2(f2 a) { return a ^ 0x8000000080000000ull; }
 
-// NaN-propagating three-input min/max (FMNMX3.NAN): an invalid cell poisons the window result.
+// Three-input min/max (FMNMX3) with IEEE minNum/maxNum semantics: NaN operands are skipped, which is
+// exactly how the reference's step filter treats invalid cells (StepFilter.cpp:126,159); the result is
+// NaN only when every operand is.  Excluded on-circle tips are passed as NaN.
 __device__ __forceinline__ float max3n(float a, float b, float c) {
   float r;
-  asm("max.NaN.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
   return r;
 }
 __device__ __forceinline__ float min3n(float a, float b, float c) {
   float r;
-  asm("min.NaN.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
+// 1.0f / 0.0f comparison result in one instruction (FSET.BF)
+__device__ __forceinline__ float gtf(float a, float b) {
+  float r;
+  asm("set.gt.f32.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ float rcp_a(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float rsq_a(float x) {
+  float r;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float sqrt_a(float x) {
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
   return r;
 }
 
 // ---------------------------------------------------------------------------------------------
-// mbarrier / TMA (per-warp pipelines)
+// shared memory / mbarrier / TMA (per-warp pipelines), all on 32-bit shared addresses
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ f2 lds64(unsigned a) {
+  f2 v;
+  asm volatile("ld.shared.b64 %0, [%1];" : "=l"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts64(unsigned a, float x, float y) {
+  asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(a), "f"(x), "f"(y) : "memory");
+}
 __device__ __forceinline__ void mbar_init(unsigned bar, int count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
@@ -177,17 +226,14 @@ __device__ __forceinline__ float colmax_w(const float* z, int r) {
   else if constexpr (W == 1) return max3n(z[r + 1], z[r + 2], z[r + 3]);
   else return max3n(max3n(z[r + 1], z[r + 2], z[r + 3]), z[r], z[r + 4]);
 }
+// count (as float) of rows whose flag f[] is set
 template <int W>
-__device__ __forceinline__ int colcnt_w(const float* z, int r, float crit) {
-  int c = z[r + 2] > crit;
-  if constexpr (W >= 1) c += (z[r + 1] > crit) + (z[r + 3] > crit);
-  if constexpr (W >= 2) c += (z[r] > crit) + (z[r + 4] > crit);
+__device__ __forceinline__ float colcnt_w(const float* f, int r) {
+  float c = f[r + 2];
+  if constexpr (W >= 1) c += f[r + 1] + f[r + 3];
+  if constexpr (W >= 2) c += f[r] + f[r + 4];
   return c;
 }
-
-struct i2 {
-  int x, y;
-};
 
 // Per-lane register state.  Rings are indexed by the arrival phase of the column (0..4).
 template <class S>
@@ -198,193 +244,208 @@ struct Lane {
   f2 c1mn[5], c1mx[5];               // pass-1 column min/max of width W11 (columns l = +-1)
   f2 p1mn[5], p1mx[5];               // pass-1 centre column (width W10 + masked tips)
   f2 sh[5];                          // own-row step_height
-  f2 s3mx[5];                        // pass-2 column max of width W21
-  f2 pcmx[5];                        // pass-2 centre column
-  i2 s3c[5], pcc[5];                 // matching counts of step_height > critical
+  f2 s3mx[5], s3c[5];                // pass-2 column max / count of width W21
+  f2 pcmx[5], pcc[5];                // pass-2 centre column
   f2 dslope[5], drough[5];           // slope / roughness layers waiting for the step layer
-  i2 dflag[5];                       // certification flags of the normals stage
+  unsigned dflag[5];                 // certification flags of the normals stage (bit0 row x, bit1 row y)
 };
 
 template <int W, class S>
 __device__ __forceinline__ f2 runA(const Lane<S>& L, int s) {
   if constexpr (W == 2) return L.a2[s];
   else if constexpr (W == 1) return L.a1[s];
-  else return f2{0.f, 0.f};
+  else return 0ull;
 }
 template <int W, class S>
 __device__ __forceinline__ f2 runB(const Lane<S>& L, int s) {
   if constexpr (W == 2) return L.b2[s];
   else if constexpr (W == 1) return L.b1[s];
-  else return f2{0.f, 0.f};
+  else return 0ull;
 }
 template <int W, class S>
 __device__ __forceinline__ f2 runQ(const Lane<S>& L, int s) {
   if constexpr (W == 2) return L.q2[s];
   else if constexpr (W == 1) return L.q1[s];
-  else return f2{0.f, 0.f};
+  else return 0ull;
 }
 
-__device__ __forceinline__ float rsqrt_nr(float x) {  // rsqrt with one Newton step (rel. error ~1e-7)
-  float r = rsqrtf(x);
-  return r * fmaf(-0.5f * x, r * r, 1.5f);
-}
-
-struct NormalOut {
-  float nx, ny, nz, slope, rough;
-  int flag;
+struct Normal2 {
+  f2 nx, ny, nz, slope, rough;
+  unsigned flag;  // bit0: row x, bit1: row y could not be certified
 };
 
-// Closed-form smallest eigenpair of [[a,0,p],[0,a,q],[p,q,c]] + certification (one row).
-__device__ __forceinline__ NormalOut finish_normal(const FusedArgs& A, float Sw, float Sk, float Sl, float Sww) {
-  NormalOut o;
-  const float mw = Sw * A.invN;
-  const float c = fmaf(-mw, mw, Sww * A.invN);  // Czz
-  const float p = A.kp * Sk, q = A.kp * Sl;       // Cxz, Cyz
-  const float g2 = fmaf(p, p, q * q);
-  const float h = 0.5f * (A.a_cov - c);
-  const float hh = fmaf(h, h, g2);
-  float D = hh * rsqrtf(hh);
-  D = (hh > 0.f) ? fmaf(0.5f * (hh - D * D), __frcp_rn(D), D) : 0.f;  // sqrt with one correction
-  const float dph = D + fabsf(h);
-  const float qq = (dph > 0.f) ? __fdividef(g2, dph) : 0.f;
-  const float qq2 = (dph > 0.f) ? fmaf(fmaf(-qq, dph, g2), __frcp_rn(dph), qq) : 0.f;  // refined g2/dph
-  const bool hpos = h >= 0.f;
-  const float m = hpos ? dph : qq2;                       // a - lambda0
-  float lam0 = hpos ? (c - qq2) : (A.a_cov - qq2);       // smallest eigenvalue
-  const float nn = fmaf(m, m, g2);
-  const float rn = rsqrt_nr(nn);
-  o.nx = -p * rn;
-  o.ny = -q * rn;
-  float nz = m * rn;
-  int flag = 0;
-  // invalid window (NaN/Inf poisoning, overflow) or degenerate pencil
-  if (!(fabsf(Sww) < 3.0e38f) || !(nn > 0.f)) flag = 1;
-  // small inclination: n_z = 1 - s with s from tan^2; certify the float32 rounding of n_z where
-  // acos amplifies one ulp beyond the tolerance (theta < ~0.012 rad)
-  const float t = g2 * __frcp_rn(m * m);
-  if (hpos && t < 2.5e-3f) {
-    const float s = t * fmaf(-t, fmaf(-0.3125f, t, 0.375f), 0.5f);
-    nz = 1.0f - s;
-    if (s < 7.2e-5f) {
-      const float qv = s * 16777216.0f;
+// acos on [0,1] for both rows: 2*asin(sqrt((1-x)/2)) above 0.5, pi/2 - asin(x) below; asin by a
+// degree-4 polynomial in y^2 on [0, 0.5] (max rel. error 7e-8, fitted offline).
+__device__ __forceinline__ f2 acos2(const FusedArgs& A, f2 x) {
+  const f2 u = fma2(x, A.k_mhalf, A.k_half);
+  const f2 xx = mul2(x, x);
+  const float x0 = lo(x), x1 = hi(x);
+  const bool bx = x0 >= 0.5f, by = x1 >= 0.5f;
+  const f2 y2 = mk(bx ? lo(u) : lo(xx), by ? hi(u) : hi(xx));
+  const f2 y = mk(bx ? sqrt_a(lo(u)) : x0, by ? sqrt_a(hi(u)) : x1);
+  f2 p = fma2(y2, A.k_p4, A.k_p3);
+  p = fma2(p, y2, A.k_p2);
+  p = fma2(p, y2, A.k_p1);
+  p = fma2(p, y2, A.k_p0);
+  const f2 a = fma2(mul2(y, y2), p, y);
+  const f2 sc = mk(bx ? 2.0f : -1.0f, by ? 2.0f : -1.0f);
+  const f2 of = mk(bx ? 0.0f : 1.5707963267948966f, by ? 0.0f : 1.5707963267948966f);
+  return fma2(a, sc, of);
+}
+
+// Closed-form smallest eigenpair of the scatter matrix [[a,0,p],[0,a,q],[p,q,c]] of a full disk
+// window for both rows of the lane, slope and roughness layers, and the certification of all of it.
+__device__ __forceinline__ Normal2 finish_normal2(const FusedArgs& A, f2 Sw, f2 Sk, f2 Sl, f2 Sww, f2 ec) {
+  Normal2 o;
+  const f2 mw = mul2(Sw, A.k_invN);
+  const f2 c = fma2(mul2(Sw, A.k_minvN), mw, mul2(Sww, A.k_invN));  // Czz = Sww/N - (Sw/N)^2
+  const f2 p = mul2(Sk, A.k_kp), q = mul2(Sl, A.k_kp);               // Cxz, Cyz
+  const f2 g2 = fma2(p, p, mul2(q, q));
+  const f2 h = fma2(c, A.k_mhalf, A.k_half_a);                        // (a - c)/2
+  const f2 hh = fma2(h, h, g2);
+  const f2 rD = mk(rsq_a(lo(hh)), rsq_a(hi(hh)));
+  const f2 D0 = mul2(hh, rD);
+  const f2 D = fma2(fma2(mul2(D0, A.k_mone), D0, hh), mul2(rD, A.k_half), D0);  // sqrt(hh), one correction
+  const float h0 = lo(h), h1 = hi(h);
+  const f2 dph = add2(D, mk(fabsf(h0), fabsf(h1)));
+  const f2 rq = mk(rcp_a(lo(dph)), rcp_a(hi(dph)));
+  const f2 q0 = mul2(g2, rq);
+  const f2 qq = fma2(fma2(mul2(q0, A.k_mone), dph, g2), rq, q0);  // g2 / dph, one correction
+  const bool hx = h0 >= 0.f, hy = h1 >= 0.f;
+  const f2 m = mk(hx ? lo(dph) : lo(qq), hy ? hi(dph) : hi(qq));  // a - lambda0
+  const f2 cmag = mk(hx ? lo(c) : A.a_cov, hy ? hi(c) : A.a_cov);
+  const f2 lam0 = sub2(cmag, qq);                                  // smallest eigenvalue
+  const f2 m2 = mul2(m, m);
+  const f2 nn = add2(m2, g2);
+  const f2 r0 = mk(rsq_a(lo(nn)), rsq_a(hi(nn)));
+  const f2 rn = mul2(r0, fma2(mul2(mul2(nn, A.k_mhalf), r0), r0, A.k_1p5));  // rsqrt(nn), one Newton step
+  const f2 nrn = mul2(rn, A.k_mone);
+  o.nx = mul2(p, nrn);
+  o.ny = mul2(q, nrn);
+  const f2 nzg = mul2(m, rn);
+  // roughness = sqrt(lambda0 * N/(N-1)); lambda0 is a difference of two terms of size cmag
+  const f2 rr2 = mul2(lam0, A.k_nnm1);
+  const f2 r = mk(sqrt_a(fmaxf(lo(rr2), 0.f)), sqrt_a(fmaxf(hi(rr2), 0.f)));
+  const f2 thr = mul2(mul2(cmag, cmag), A.k_rough_thr);
+  // small inclination: n_z = 1 - s with s from t = tan^2(theta) (series; exact rounding of 1 - s)
+  const f2 rm = mk(rcp_a(lo(m2)), rcp_a(hi(m2)));
+  const f2 t0 = mul2(g2, rm);
+  const f2 t = fma2(fma2(mul2(t0, A.k_mone), m2, g2), rm, t0);
+  const f2 s = mul2(t, fma2(mul2(t, A.k_mone), fma2(t, A.k_m03125, A.k_0375), A.k_half));
+  const f2 nzs = sub2(A.k_one, s);
+  const bool smx = hx && lo(t) < 2.5e-3f, smy = hy && hi(t) < 2.5e-3f;
+  const f2 nz = mk(fminf(smx ? lo(nzs) : lo(nzg), 1.0f), fminf(smy ? hi(nzs) : hi(nzg), 1.0f));
+  unsigned flag = 0;
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    auto R = [&](f2 v) { return k ? hi(v) : lo(v); };
+    const float sww = R(Sww), cm = R(cmag);
+    // invalid window (NaN/Inf poisoning, overflow) or degenerate pencil
+    const bool b_inv = !(sww < 3.0e38f) || !(R(nn) > 0.f);
+    bool bad = b_inv;
+    // rank / roughness: lambda0 must stand clear of the cancellation error (1e-5 cmag), of the
+    // reference's rank-threshold region (1e-10 a) and of what the roughness tolerance allows;
+    // conditioning: eigen-gap min(2D, m) against the matrix scale.  Exactly flat windows are exact.
+    const float lthr = fmaxf(fmaxf(1e-5f * cm, 1e-10f * A.a_cov), R(thr));
+    const float gap = fminf(2.0f * R(D), R(m));
+    const bool b_lam = (sww > 0.f) && !(R(lam0) > lthr);
+    const bool b_cond = (sww > 0.f) && gap < A.cond_k * fmaxf(A.a_cov, R(c));
+    bad |= b_lam || b_cond;
+    flag |= bad ? (1u << k) : 0u;
+    if (A.stats) flag |= ((b_inv ? 1u : 0u) | (b_lam ? 2u : 0u) | (b_cond ? 4u : 0u)) << (2 + 4 * k);
+  }
+  // where acos amplifies one ulp of n_z beyond the tolerance (theta < ~0.012 rad) certify its rounding
+  const bool cx = smx && lo(s) < 7.2e-5f && lo(Sww) > 0.f, cy = smy && hi(s) < 7.2e-5f && hi(Sww) > 0.f;
+  if (cx || cy) {
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      auto R = [&](f2 v) { return k ? hi(v) : lo(v); };
+      if (!(k ? cy : cx)) continue;
+      const float qv = R(s) * 16777216.0f;
       const float fr = qv - floorf(qv);
-      // relative error bound of s: first moments carry <= 2.5e-6*sqrt(Sww) absolute error
-      const float gm = sqrtf(fmaf(Sk, Sk, Sl * Sl));
-      const float eps = fmaf(7.1e-6f, sqrtf(Sww) * __frcp_rn(fmaxf(gm, 1e-30f)), 2e-6f);
-      if (fabsf(fr - 0.5f) <= fmaf(qv, eps, 1e-3f) && Sww > 0.f) flag = 1;
+      // relative error bound of s: the first moments carry <= 2.5e-6*sqrt(Sww) absolute error
+      const float gm2 = fmaf(R(Sk), R(Sk), R(Sl) * R(Sl));
+      const float eps = fmaf(7.1e-6f, sqrt_a(R(Sww) * rcp_a(fmaxf(gm2, 1e-36f))), 2e-6f);
+      if (fabsf(fr - 0.5f) <= fmaf(qv, eps, 1e-3f)) flag |= (1u << k) | (A.stats ? (8u << (2 + 4 * k)) : 0u);
     }
   }
-  // numerically rank-deficient scatter (exactly planar data): the reference's rank test decides.
-  // lambda0 is the difference of two terms of size cmag, each carrying ~1e-6 relative error.
-  const float cmag = hpos ? c : A.a_cov;
-  if (Sww > 0.f && !(lam0 > 1e-5f * cmag && lam0 > 1e-10f * A.a_cov)) flag = 1;
-  lam0 = fmaxf(lam0, 0.f);
-  const float r = sqrtf(lam0 * A.n_over_nm1);
-  // roughness layer error = d(lambda0) * N/(N-1) / (2 r crit) with d(lambda0) ~ 1.1e-6 cmag; keep it < 3e-6
-  if (Sww > 0.f && r * A.rough_crit < 0.2f * cmag) flag = 1;
-  // eigenvector conditioning: the gap to the other two eigenvalues is min(2D, m); when it is small
-  // against the matrix scale the fp32 moment errors are amplified beyond the tolerance
-  if (Sww > 0.f && fminf(2.0f * D, m) < 0.25f * fmaxf(A.a_cov, c)) flag = 1;
-  nz = fminf(nz, 1.0f);
-  const float theta = acosf(nz);
+  const f2 theta = acos2(A, nz);
   o.nz = nz;
-  o.slope = theta < A.slope_crit ? fmaf(-theta, A.inv_slope_crit, 1.0f) : 0.0f;
-  o.rough = r < A.rough_crit ? fmaf(-r, A.inv_rough_crit, 1.0f) : 0.0f;
+  // layer = x < crit ? 1 - x/crit : 0  ==  max(1 - x/crit, 0)
+  const f2 sl = fma2(theta, A.k_minv_slope, A.k_one);
+  const f2 ro = fma2(r, A.k_minv_rough, A.k_one);
+  // a hole (invalid centre) has no normal: slope and roughness stay NaN and nothing needs certifying
+  // (SlopeFilter.cpp:71, RoughnessFilter.cpp:84)
+  const float e0 = lo(ec), e1 = hi(ec);
+  const bool v0 = fabsf(e0) < 3.0e38f, v1 = fabsf(e1) < 3.0e38f;
+  const float qn = __int_as_float(0x7fc00000);
+  o.slope = mk(v0 ? fmaxf(lo(sl), 0.0f) : qn, v1 ? fmaxf(hi(sl), 0.0f) : qn);
+  o.rough = mk(v0 ? fmaxf(lo(ro), 0.0f) : qn, v1 ? fmaxf(hi(ro), 0.0f) : qn);
+  if (!v0) { flag &= ~0x3du; o.nx = mk(qn, hi(o.nx)); o.ny = mk(qn, hi(o.ny)); o.nz = mk(qn, hi(o.nz)); }
+  if (!v1) { flag &= ~0x3c2u; o.nx = mk(lo(o.nx), qn); o.ny = mk(lo(o.ny), qn); o.nz = mk(lo(o.nz), qn); }
   o.flag = flag;
   return o;
+}
+
+// Rare paths kept out of line so that the five unrolled march phases stay small.
+__device__ __noinline__ void append_flagged(unsigned* count, unsigned* list, unsigned cap, int lane, unsigned cell, unsigned fl0, unsigned fl1, unsigned cat) {
+  if (cat >> 2) {
+    const unsigned c0 = (cat >> 2) & 15u, c1 = (cat >> 6) & 15u;
+    const unsigned nl = ((c0 >> 1) & 1u) + ((c1 >> 1) & 1u), nc = ((c0 >> 2) & 1u) + ((c1 >> 2) & 1u), ns = ((c0 >> 3) & 1u) + ((c1 >> 3) & 1u);
+    if (nl) atomicAdd(count + 1, nl);
+    if (nc) atomicAdd(count + 2, nc);
+    if (ns) atomicAdd(count + 3, ns);
+  }
+  const unsigned b0 = __ballot_sync(FULL, fl0 != 0u), b1 = __ballot_sync(FULL, fl1 != 0u);
+  unsigned base = 0;
+  if (lane == 0) base = atomicAdd(count, (unsigned)(__popc(b0) + __popc(b1)));
+  base = __shfl_sync(FULL, base, 0);
+  const unsigned lower = (1u << lane) - 1u;
+  if (fl0) {
+    const unsigned idx = base + __popc(b0 & lower);
+    if (idx < cap) list[idx] = cell | (fl0 << 30);
+  }
+  if (fl1) {
+    const unsigned idx = base + __popc(b0) + __popc(b1 & lower);
+    if (idx < cap) list[idx] = (cell + 1u) | (fl1 << 30);
+  }
+}
+__device__ __noinline__ void store_normals(float* pnx, float* pny, float* pnz, bool ok, size_t oc, f2 nx, f2 ny, f2 nz) {
+  if (!ok) return;
+  *reinterpret_cast<f2*>(pnx + oc) = nx;
+  *reinterpret_cast<f2*>(pny + oc) = ny;
+  *reinterpret_cast<f2*>(pnz + oc) = nz;
 }
 
 template <class S>
 struct StepCtx {
   const FusedArgs& A;
-  const CUtensorMap* map;
-  float* ering;     // NST stages
-  float* shbuf;     // 2 x SHBUF_FLOATS
-  unsigned bar0;    // shared address of the first stage barrier
+  unsigned e_lane;    // shared address of the lane's first staged row in stage 0 / column 0
+  unsigned sh_lane;   // shared address of the lane's first step_height row in buffer 0
   int lane;
-  int s0;           // first row of the strip
-  int q0, q1;       // output columns of the unit
+  int s0;             // first row held by the warp (strip row 0 = output row -2)
+  int q0, q1;         // output columns of the unit
   unsigned rm0, rm1;  // row masks of the lane's two rows
-  unsigned rmx;       // row mask of the extra row handled by lanes 0..3
-  int xrow;           // strip-relative row (-2,-1,64,65) of the extra row
+  bool out_ok;        // lane produces output rows (lanes 1..30 and inside the map)
+  size_t oc;          // running output offset (column jo, lane's first row)
+  size_t ocn;         // same for the normals stage (column jn)
 };
-
-// step_height of one arbitrary strip row at column `js`, straight from the staged elevation
-// (used by lanes 0..3 for the four halo rows of the exchange buffer).
-template <class S>
-__device__ __noinline__ float sh_direct(const StepCtx<S>& C, int t, unsigned kc_stage_base, unsigned cmask) {
-  // columns js-2..js+2 are the ones that arrived at steps t-4..t
-  float col[5][5];
-  const int er = C.xrow + 4;  // row inside the staged window
-#pragma unroll
-  for (int a = 0; a < 5; ++a) {
-    const int tt = t - a;  // arrival step of column js+2-a
-    const int chunk = tt / CH, slot = tt - chunk * CH;
-    const float* base = C.ering + ((kc_stage_base + chunk) % NST) * STAGE_FLOATS + slot * EROWS + er;
-#pragma unroll
-    for (int k = 0; k < 5; ++k) col[a][k] = base[k - 2];
-  }
-  // col[a] : a=0 -> js+2, a=2 -> js, a=4 -> js-2 ; col[a][2] centre row
-  const float z0 = col[2][2];
-  float mn, mx;
-  {
-    const float* c = col[2];
-    float lo = min3n(c[1], c[2], c[3]), hi = max3n(c[1], c[2], c[3]);
-    if constexpr (S::W10 == 2) {
-      lo = min3n(lo, c[0], c[4]);
-      hi = max3n(hi, c[0], c[4]);
-    } else if constexpr (S::TIP1) {
-      const float tu = (C.rmx & 1u) ? c[0] : z0, td = (C.rmx & 2u) ? c[4] : z0;
-      lo = min3n(lo, tu, td);
-      hi = max3n(hi, tu, td);
-    }
-    mn = lo;
-    mx = hi;
-  }
-  if constexpr (S::W11 >= 0) {
-    const float* cl = col[3];
-    const float* cr = col[1];
-    float l0, l1, h0, h1;
-    if constexpr (S::W11 == 0) { l0 = h0 = cl[2]; l1 = h1 = cr[2]; }
-    else if constexpr (S::W11 == 1) {
-      l0 = min3n(cl[1], cl[2], cl[3]); h0 = max3n(cl[1], cl[2], cl[3]);
-      l1 = min3n(cr[1], cr[2], cr[3]); h1 = max3n(cr[1], cr[2], cr[3]);
-    } else {
-      l0 = min3n(min3n(cl[1], cl[2], cl[3]), cl[0], cl[4]); h0 = max3n(max3n(cl[1], cl[2], cl[3]), cl[0], cl[4]);
-      l1 = min3n(min3n(cr[1], cr[2], cr[3]), cr[0], cr[4]); h1 = max3n(max3n(cr[1], cr[2], cr[3]), cr[0], cr[4]);
-    }
-    mn = min3n(mn, l0, l1);
-    mx = max3n(mx, h0, h1);
-  }
-  if constexpr (S::W12 == 0 || S::TIP1) {
-    float tl = col[4][2], tr = col[0][2];
-    if constexpr (S::TIP1) {
-      tl = (cmask & 1u) ? tl : z0;
-      tr = (cmask & 2u) ? tr : z0;
-    }
-    mn = min3n(mn, tl, tr);
-    mx = max3n(mx, tl, tr);
-  }
-  return mx - mn;
-}
 
 // One march step: column ce = q0 - 4 + t arrives.  PH = t % 5.
 template <class S, int PH>
-__device__ __forceinline__ void march_step(const StepCtx<S>& C, Lane<S>& L, int t, unsigned stage_of_chunk, unsigned kc_stage_base,
-                                           unsigned cm_js, unsigned cm_jo) {
+__device__ __forceinline__ void march_step(StepCtx<S>& C, Lane<S>& L, int t, unsigned stage, unsigned cm_js, unsigned cm_jo) {
   const FusedArgs& A = C.A;
   constexpr int S0 = PH, S1 = (PH + 4) % 5, S2 = (PH + 3) % 5, S3 = (PH + 2) % 5, S4 = (PH + 1) % 5;  // slot of age 0..4
   const int ce = C.q0 - 4 + t;
   // ---- stage A: the arriving elevation column -------------------------------------------------
   float z[6];
+  f2 ZM2, Z0, ZP2;
   {
-    const float* col = C.ering + stage_of_chunk * STAGE_FLOATS + PH * EROWS + 2 + 2 * C.lane;  // staged row 0 is strip row -4
-    const float2 v0 = *reinterpret_cast<const float2*>(col);
-    const float2 v1 = *reinterpret_cast<const float2*>(col + 2);
-    const float2 v2 = *reinterpret_cast<const float2*>(col + 4);
-    z[0] = v0.x; z[1] = v0.y; z[2] = v1.x; z[3] = v1.y; z[4] = v2.x; z[5] = v2.y;
+    const unsigned a = C.e_lane + stage * STAGE_BYTES + PH * (EROWS * 4);
+    ZM2 = lds64(a); Z0 = lds64(a + 8); ZP2 = lds64(a + 16);
+    z[0] = lo(ZM2); z[1] = hi(ZM2); z[2] = lo(Z0); z[3] = hi(Z0); z[4] = lo(ZP2); z[5] = hi(ZP2);
   }
-  const f2 Z0{z[2], z[3]}, ZM1{z[1], z[2]}, ZP1{z[3], z[4]}, ZM2{z[0], z[1]}, ZP2{z[4], z[5]};
+  const f2 ZM1 = mk(z[1], z[2]), ZP1 = mk(z[3], z[4]);
   L.e[S0] = Z0;
   if constexpr (S::NEED_N1 || S::NEED_N2) {
     const f2 D1 = sub2(ZP1, Z0), Dm1 = sub2(ZM1, Z0);
@@ -395,7 +456,7 @@ __device__ __forceinline__ void march_step(const StepCtx<S>& C, Lane<S>& L, int 
     if constexpr (S::NEED_N2) {
       const f2 D2 = sub2(ZP2, Z0), Dm2 = sub2(ZM2, Z0);
       L.a2[S0] = add2(A1, add2(D2, Dm2));
-      L.b2[S0] = fma2(sub2(ZP2, ZM2), bc(2.0f), B1);
+      L.b2[S0] = fma2(sub2(ZP2, ZM2), A.k_two, B1);
       L.q2[S0] = fma2(D2, D2, fma2(Dm2, Dm2, Q1));
     }
   }
@@ -403,32 +464,35 @@ __device__ __forceinline__ void march_step(const StepCtx<S>& C, Lane<S>& L, int 
     float cmn[2], cmx[2], pmn[2], pmx[2];
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
-      if constexpr (S::W11 >= 0) { cmn[r] = colmin_w<(S::W11 < 0 ? 0 : S::W11)>(z, r); cmx[r] = colmax_w<(S::W11 < 0 ? 0 : S::W11)>(z, r); }
+      const float lo3 = min3n(z[r + 1], z[r + 2], z[r + 3]), hi3 = max3n(z[r + 1], z[r + 2], z[r + 3]);
+      if constexpr (S::W11 == 1) { cmn[r] = lo3; cmx[r] = hi3; }
+      else if constexpr (S::W11 >= 0) { cmn[r] = colmin_w<(S::W11 < 0 ? 0 : S::W11)>(z, r); cmx[r] = colmax_w<(S::W11 < 0 ? 0 : S::W11)>(z, r); }
       else { cmn[r] = cmx[r] = 0.f; }
-      float lo = min3n(z[r + 1], z[r + 2], z[r + 3]), hi = max3n(z[r + 1], z[r + 2], z[r + 3]);
+      float mn = lo3, mx = hi3;
       if constexpr (S::W10 == 2) {
-        lo = min3n(lo, z[r], z[r + 4]);
-        hi = max3n(hi, z[r], z[r + 4]);
+        mn = min3n(mn, z[r], z[r + 4]);
+        mx = max3n(mx, z[r], z[r + 4]);
       } else if constexpr (S::TIP1) {
         const unsigned rm = r ? C.rm1 : C.rm0;
-        const float tu = (rm & 1u) ? z[r] : z[r + 2], td = (rm & 2u) ? z[r + 4] : z[r + 2];
-        lo = min3n(lo, tu, td);
-        hi = max3n(hi, tu, td);
+        const float qn = __int_as_float(0x7fc00000);
+        const float tu = (rm & 1u) ? z[r] : qn, td = (rm & 2u) ? z[r + 4] : qn;
+        mn = min3n(mn, tu, td);
+        mx = max3n(mx, tu, td);
       }
-      pmn[r] = lo;
-      pmx[r] = hi;
+      pmn[r] = mn;
+      pmx[r] = mx;
     }
-    L.c1mn[S0] = f2{cmn[0], cmn[1]}; L.c1mx[S0] = f2{cmx[0], cmx[1]};
-    L.p1mn[S0] = f2{pmn[0], pmn[1]}; L.p1mx[S0] = f2{pmx[0], pmx[1]};
+    L.c1mn[S0] = mk(cmn[0], cmn[1]); L.c1mx[S0] = mk(cmx[0], cmx[1]);
+    L.p1mn[S0] = mk(pmn[0], pmn[1]); L.p1mx[S0] = mk(pmx[0], pmx[1]);
   }
   if (t < 4) return;  // rings not primed yet
   // ---- stage B: step_height of column js = ce - 2 (ages: js+1 -> 1, js -> 2, js-1 -> 3) ---------
-  float* shcol = C.shbuf + (t & 1) * SHBUF_FLOATS;
+  const unsigned shcol = C.sh_lane + (t & 1) * SHBUF_BYTES;
   {
     float shv[2];
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
-      auto R = [&](const f2& v) { return r ? v.y : v.x; };
+      auto R = [&](f2 v) { return r ? hi(v) : lo(v); };
       float mn = R(L.p1mn[S2]), mx = R(L.p1mx[S2]);
       if constexpr (S::W11 >= 0) {
         mn = min3n(mn, R(L.c1mn[S1]), R(L.c1mn[S3]));
@@ -437,71 +501,66 @@ __device__ __forceinline__ void march_step(const StepCtx<S>& C, Lane<S>& L, int 
       if constexpr (S::W12 == 0 || S::TIP1) {
         float tl = R(L.e[S4]), tr = R(L.e[S0]);
         if constexpr (S::TIP1) {
-          const float z0 = R(L.e[S2]);
-          tl = (cm_js & 1u) ? tl : z0;
-          tr = (cm_js & 2u) ? tr : z0;
+          const float qn = __int_as_float(0x7fc00000);
+          tl = (cm_js & 1u) ? tl : qn;
+          tr = (cm_js & 2u) ? tr : qn;
         }
         mn = min3n(mn, tl, tr);
         mx = max3n(mx, tl, tr);
       }
-      shv[r] = mx - mn;
+      // centre gate (StepFilter.cpp:113): an invalid centre (NaN, or Inf: Inf - Inf) leaves step_height NaN
+      const float zc = R(L.e[S2]);
+      shv[r] = (mx - mn) + (zc - zc);
     }
-    *reinterpret_cast<float2*>(shcol + 2 + 2 * C.lane) = make_float2(shv[0], shv[1]);
-    if (C.lane < 4) {
-      const float x = sh_direct<S>(C, t, kc_stage_base, cm_js);
-      shcol[C.xrow + 2] = x;
-    }
+    sts64(shcol + 8, shv[0], shv[1]);  // buffer row 0 is strip row -2
   }
   __syncwarp();
-  float v[6];
+  float v[6], f[6];
+  f2 V0;
   {
-    const float* p = shcol + 2 * C.lane;
-    const float2 v0 = *reinterpret_cast<const float2*>(p);
-    const float2 v1 = *reinterpret_cast<const float2*>(p + 2);
-    const float2 v2 = *reinterpret_cast<const float2*>(p + 4);
-    v[0] = v0.x; v[1] = v0.y; v[2] = v1.x; v[3] = v1.y; v[4] = v2.x; v[5] = v2.y;
+    const f2 VM2 = lds64(shcol), VP2 = lds64(shcol + 16);
+    V0 = lds64(shcol + 8);
+    v[0] = lo(VM2); v[1] = hi(VM2); v[2] = lo(V0); v[3] = hi(V0); v[4] = lo(VP2); v[5] = hi(VP2);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) f[k] = gtf(v[k], A.step_crit);
   }
   {
-    float smx[2], pmx[2];
-    int sc[2], pc[2];
+    float smx[2], pmx[2], sc[2], pc[2];
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
-      if constexpr (S::W21 >= 0) {
-        smx[r] = colmax_w<(S::W21 < 0 ? 0 : S::W21)>(v, r);
-        sc[r] = colcnt_w<(S::W21 < 0 ? 0 : S::W21)>(v, r, A.step_crit);
-      } else { smx[r] = 0.f; sc[r] = 0; }
-      float hi = max3n(v[r + 1], v[r + 2], v[r + 3]);
-      int cnt = (v[r + 1] > A.step_crit) + (v[r + 2] > A.step_crit) + (v[r + 3] > A.step_crit);
+      const float hi3 = max3n(v[r + 1], v[r + 2], v[r + 3]);
+      const float c3 = f[r + 1] + f[r + 2] + f[r + 3];
+      if constexpr (S::W21 == 1) { smx[r] = hi3; sc[r] = c3; }
+      else if constexpr (S::W21 >= 0) { smx[r] = colmax_w<(S::W21 < 0 ? 0 : S::W21)>(v, r); sc[r] = colcnt_w<(S::W21 < 0 ? 0 : S::W21)>(f, r); }
+      else { smx[r] = 0.f; sc[r] = 0.f; }
+      float mx = hi3, cnt = c3;
       if constexpr (S::W20 == 2) {
-        hi = max3n(hi, v[r], v[r + 4]);
-        cnt += (v[r] > A.step_crit) + (v[r + 4] > A.step_crit);
+        mx = max3n(mx, v[r], v[r + 4]);
+        cnt += f[r] + f[r + 4];
       } else if constexpr (S::TIP2) {
         const unsigned rm = r ? C.rm1 : C.rm0;
         const bool iu = rm & 4u, id = rm & 8u;
-        hi = max3n(hi, iu ? v[r] : v[r + 2], id ? v[r + 4] : v[r + 2]);
-        cnt += (iu && v[r] > A.step_crit) + (id && v[r + 4] > A.step_crit);
+        const float qn = __int_as_float(0x7fc00000);
+        mx = max3n(mx, iu ? v[r] : qn, id ? v[r + 4] : qn);
+        cnt += (iu ? f[r] : 0.f) + (id ? f[r + 4] : 0.f);
       }
-      pmx[r] = hi;
+      pmx[r] = mx;
       pc[r] = cnt;
     }
-    L.sh[S0] = f2{v[2], v[3]};
-    L.s3mx[S0] = f2{smx[0], smx[1]}; L.s3c[S0] = i2{sc[0], sc[1]};
-    L.pcmx[S0] = f2{pmx[0], pmx[1]}; L.pcc[S0] = i2{pc[0], pc[1]};
+    L.sh[S0] = V0;
+    L.s3mx[S0] = mk(smx[0], smx[1]); L.s3c[S0] = mk(sc[0], sc[1]);
+    L.pcmx[S0] = mk(pmx[0], pmx[1]); L.pcc[S0] = mk(pc[0], pc[1]);
   }
   // ---- normals / slope / roughness of column jn = ce - 2 (ages: l = 2 - age) -------------------
   const int jn = ce - 2;
-  const int row0 = C.s0 + 2 * C.lane;
-  const bool rows_ok = row0 < A.rows;
   if (jn >= C.q0 && jn < C.q1) {
-    constexpr int m0 = S::WN2 >= 0 ? 2 * S::WN2 + 1 : 0;  // cells in the columns at l = +-2
-    constexpr int m1 = S::WN1 >= 0 ? 2 * S::WN1 + 1 : 0;
     const f2 ec = L.e[S2];
     f2 Sw = runA<S::WN0>(L, S2), Sk = runB<S::WN0>(L, S2), Sww = runQ<S::WN0>(L, S2);
-    f2 Sl{0.f, 0.f};
+    f2 Sl = 0ull;
     if constexpr (S::WN1 >= 0) {
       const f2 dR = sub2(L.e[S1], ec), dL = sub2(L.e[S3], ec);
       const f2 aR = runA<S::WN1>(L, S1), aL = runA<S::WN1>(L, S3);
-      const f2 tR = fma2(bc((float)m1), dR, aR), tL = fma2(bc((float)m1), dL, aL);
+      const f2 tR = fma2(A.k_m1, dR, aR), tL = fma2(A.k_m1, dL, aL);
       Sw = add2(Sw, add2(tR, tL));
       Sl = sub2(tR, tL);
       Sk = add2(Sk, add2(runB<S::WN1>(L, S1), runB<S::WN1>(L, S3)));
@@ -511,25 +570,20 @@ __device__ __forceinline__ void march_step(const StepCtx<S>& C, Lane<S>& L, int 
     if constexpr (S::WN2 >= 0) {
       const f2 dR = sub2(L.e[S0], ec), dL = sub2(L.e[S4], ec);
       const f2 aR = runA<S::WN2>(L, S0), aL = runA<S::WN2>(L, S4);
-      const f2 tR = fma2(bc((float)m0), dR, aR), tL = fma2(bc((float)m0), dL, aL);
+      const f2 tR = fma2(A.k_m0, dR, aR), tL = fma2(A.k_m0, dL, aL);
       Sw = add2(Sw, add2(tR, tL));
-      Sl = fma2(bc(2.0f), sub2(tR, tL), Sl);
+      Sl = fma2(A.k_two, sub2(tR, tL), Sl);
       Sk = add2(Sk, add2(runB<S::WN2>(L, S0), runB<S::WN2>(L, S4)));
       Sww = add2(Sww, fma2(dR, add2(aR, tR), runQ<S::WN2>(L, S0)));
       Sww = add2(Sww, fma2(dL, add2(aL, tL), runQ<S::WN2>(L, S4)));
     }
-    // column index grows toward -y and row index toward -x; kp carries the sign and 1/N
-    const NormalOut n0 = finish_normal(A, Sw.x, Sk.x, Sl.x, Sww.x);
-    const NormalOut n1 = finish_normal(A, Sw.y, Sk.y, Sl.y, Sww.y);
-    L.dslope[S0] = f2{n0.slope, n1.slope};
-    L.drough[S0] = f2{n0.rough, n1.rough};
-    L.dflag[S0] = i2{n0.flag, n1.flag};
-    if (A.nx != nullptr && rows_ok) {
-      const size_t oc = (size_t)(jn - A.out_col0) * A.rows + row0;
-      *reinterpret_cast<float2*>(A.nx + oc) = make_float2(n0.nx, n1.nx);
-      *reinterpret_cast<float2*>(A.ny + oc) = make_float2(n0.ny, n1.ny);
-      *reinterpret_cast<float2*>(A.nz + oc) = make_float2(n0.nz, n1.nz);
-    }
+    // row index grows toward -x and column index toward -y: kp carries that sign and 1/N
+    const Normal2 n = finish_normal2(A, Sw, Sk, Sl, Sww, ec);
+    L.dslope[S0] = n.slope;
+    L.drough[S0] = n.rough;
+    L.dflag[S0] = n.flag;
+    if (A.nx != nullptr) store_normals(A.nx, A.ny, A.nz, C.out_ok, C.ocn, n.nx, n.ny, n.nz);
+    C.ocn += (size_t)A.rows;
   }
   if (t < 8) return;
   // ---- stage C: step layer of column jo = ce - 4 and the fuse ----------------------------------
@@ -537,72 +591,61 @@ __device__ __forceinline__ void march_step(const StepCtx<S>& C, Lane<S>& L, int 
   if (jo >= C.q1) return;
   {
     float outv[2];
-    int sflag[2];
+    unsigned sflag = 0;
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
-      auto R = [&](const f2& x) { return r ? x.y : x.x; };
-      auto RI = [&](const i2& x) { return r ? x.y : x.x; };
+      auto R = [&](f2 x) { return r ? hi(x) : lo(x); };
       float mx = R(L.pcmx[S2]);
-      int cnt = RI(L.pcc[S2]);
+      float cnt = R(L.pcc[S2]);
       if constexpr (S::W21 >= 0) {
         mx = max3n(mx, R(L.s3mx[S1]), R(L.s3mx[S3]));
-        cnt += RI(L.s3c[S1]) + RI(L.s3c[S3]);
+        cnt += R(L.s3c[S1]) + R(L.s3c[S3]);
       }
       if constexpr (S::W22 == 0 || S::TIP2) {
-        float tl = R(L.sh[S4]), tr = R(L.sh[S0]);
+        const float tl = R(L.sh[S4]), tr = R(L.sh[S0]);
         bool il = true, ir = true;
         if constexpr (S::TIP2) {
           il = cm_jo & 4u;
           ir = cm_jo & 8u;
         }
-        const float c0 = R(L.sh[S2]);
-        mx = max3n(mx, il ? tl : c0, ir ? tr : c0);
-        cnt += (il && tl > A.step_crit) + (ir && tr > A.step_crit);
+        const float qn = __int_as_float(0x7fc00000);
+        mx = max3n(mx, il ? tl : qn, ir ? tr : qn);
+        cnt += (il ? gtf(tl, A.step_crit) : 0.f) + (ir ? gtf(tr, A.step_crit) : 0.f);
       }
-      sflag[r] = !(mx < 3.0e38f);  // NaN/Inf: some window cell was invalid -> literal path decides
+      sflag |= (mx > 3.0e38f) ? (1u << r) : 0u;  // an infinite elevation reached the window: the slow path sorts it out
       const float stepMax = fmaxf(mx, 0.0f);
-      const float st = fminf(stepMax, (float)cnt * A.inv_ncrit * stepMax);
-      outv[r] = st < A.step_crit ? fmaf(-st, A.inv_step_crit, 1.0f) : 0.0f;
+      const float st = fminf(stepMax, cnt * A.inv_ncrit * stepMax);
+      // st < crit ? 1 - st/crit : 0 ; no finite step_height in the window (mx is NaN) -> layer stays NaN (StepFilter.cpp:169)
+      outv[r] = (mx == mx) ? fmaxf(fmaf(-st, A.inv_step_crit, 1.0f), 0.0f) : mx;
     }
     const f2 sl = L.dslope[S2], ro = L.drough[S2];
-    const i2 nf = L.dflag[S2];
-    if (rows_ok) {
-      const size_t oc = (size_t)(jo - A.out_col0) * A.rows + row0;
-      *reinterpret_cast<float2*>(A.slope + oc) = make_float2(sl.x, sl.y);
-      *reinterpret_cast<float2*>(A.rough + oc) = make_float2(ro.x, ro.y);
+    const unsigned nf = L.dflag[S2];
+    if (C.out_ok) {
+      const size_t oc = C.oc;
+      *reinterpret_cast<f2*>(A.slope + oc) = sl;
+      *reinterpret_cast<f2*>(A.rough + oc) = ro;
       *reinterpret_cast<float2*>(A.step + oc) = make_float2(outv[0], outv[1]);
-      const float t0 = __fmul_rn(A.fuse_w, __fadd_rn(__fadd_rn(sl.x, outv[0]), ro.x));
-      const float t1 = __fmul_rn(A.fuse_w, __fadd_rn(__fadd_rn(sl.y, outv[1]), ro.y));
+      const float t0 = __fmul_rn(A.fuse_w, __fadd_rn(__fadd_rn(lo(sl), outv[0]), lo(ro)));
+      const float t1 = __fmul_rn(A.fuse_w, __fadd_rn(__fadd_rn(hi(sl), outv[1]), hi(ro)));
       *reinterpret_cast<float2*>(A.trav + oc) = make_float2(t0, t1);
     }
     // certified slow path: append flagged cells (bit 30: normals part, bit 31: step part)
-#pragma unroll
-    for (int r = 0; r < 2; ++r) {
-      const int nfl = r ? nf.y : nf.x;
-      const unsigned fl = (rows_ok ? ((nfl ? 1u : 0u) | (sflag[r] ? 2u : 0u)) : 0u);
-      const unsigned ballot = __ballot_sync(FULL, fl != 0u);
-      if (ballot) {
-        unsigned base = 0;
-        if (C.lane == 0) base = atomicAdd(A.count, (unsigned)__popc(ballot));
-        base = __shfl_sync(FULL, base, 0);
-        if (fl) {
-          const unsigned idx = base + __popc(ballot & ((1u << C.lane) - 1u));
-          if (idx < A.cap) A.list[idx] = ((unsigned)(jo - A.out_col0) * (unsigned)A.rows + (unsigned)(row0 + r)) | (fl << 30);
-        }
-      }
-    }
+    const unsigned fl0 = C.out_ok ? ((nf & 1u) | ((sflag & 1u) << 1)) : 0u;
+    const unsigned fl1 = C.out_ok ? (((nf >> 1) & 1u) | (sflag & 2u)) : 0u;
+    if (__any_sync(FULL, (fl0 | fl1) != 0u)) append_flagged(A.count, A.list, A.cap, C.lane, (unsigned)C.oc, fl0, fl1, A.stats ? nf : 0u);
+    C.oc += (size_t)A.rows;
   }
 }
 
 template <class S>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 1) k_chain_fused(const __grid_constant__ CUtensorMap map, FusedArgs A) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  unsigned char* wbase = smem_raw + warp * WARP_SMEM_BYTES;
-  float* ering = reinterpret_cast<float*>(wbase);
-  float* shbuf = reinterpret_cast<float*>(wbase + NST * STAGE_FLOATS * 4);
-  unsigned long long* bars = reinterpret_cast<unsigned long long*>(wbase + NST * STAGE_FLOATS * 4 + 2 * SHBUF_FLOATS * 4);
-  const unsigned bar0 = smem_u32(bars);
+  const int warp = __shfl_sync(FULL, (int)(threadIdx.x >> 5), 0);  // provably warp-uniform: uniform datapath for the control flow
+  const int lane = threadIdx.x & 31;
+  const unsigned wbase = smem_u32(smem_raw) + warp * WARP_SMEM_BYTES;
+  const unsigned ering = wbase;
+  const unsigned shbuf = wbase + NST * STAGE_BYTES;
+  const unsigned bar0 = shbuf + 2 * SHBUF_BYTES;
   if (lane == 0) {
     for (int s = 0; s < NST; ++s) mbar_init(bar0 + 8 * s, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -615,22 +658,22 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 1) k_chain_fused(const __g
   unsigned kglob = 0;  // chunks consumed so far by this warp (stage = kglob % NST, parity = (kglob / NST) & 1)
 
   Lane<S> L;
-  StepCtx<S> C{A, &map, ering, shbuf, bar0, lane, 0, 0, 0, 0u, 0u, 0u, 0};
-  C.xrow = lane < 2 ? lane - 2 : STRIP + lane - 2;
+  StepCtx<S> C{A, ering + lane * 8u, shbuf + lane * 8u, lane, 0, 0, 0, 0u, 0u, false, 0, 0};
 
   for (int unit = gwarp; unit < nunits; unit += total_warps) {
     const int strip = unit % A.nstrips, seg = unit / A.nstrips;
-    C.s0 = strip * STRIP;
+    C.s0 = strip * OROWS - 2;
     C.q0 = A.out_col0 + seg * A.seg_len;
     C.q1 = min(C.q0 + A.seg_len, A.out_col0 + A.out_ncols);
     const int nsteps = (C.q1 - C.q0) + 8;
     const int nchunks = (nsteps + CH - 1) / CH;
+    const int row0 = C.s0 + 2 * lane;
+    C.out_ok = lane >= 1 && lane <= 30 && row0 < A.rows;
+    C.oc = (size_t)(C.q0 - A.out_col0) * A.rows + row0;
+    C.ocn = C.oc;
     if constexpr (S::MASKS) {
-      const int r0 = C.s0 + 2 * lane;
-      C.rm0 = r0 < A.rows ? A.rowmask[r0] : 0u;
-      C.rm1 = r0 + 1 < A.rows ? A.rowmask[r0 + 1] : 0u;
-      const int xr = C.s0 + C.xrow;
-      C.rmx = (lane < 4 && xr >= 0 && xr < A.rows) ? A.rowmask[xr] : 0u;
+      C.rm0 = (row0 >= 0 && row0 < A.rows) ? A.rowmask[row0] : 0u;
+      C.rm1 = (row0 + 1 >= 0 && row0 + 1 < A.rows) ? A.rowmask[row0 + 1] : 0u;
     }
     __syncwarp();  // every lane is done with the previous unit's smem
     const unsigned kbase = kglob;
@@ -638,7 +681,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 1) k_chain_fused(const __g
       for (int k = 0; k < NST - 2 && k < nchunks; ++k) {
         const unsigned st = (kbase + k) % NST;
         mbar_expect_tx(bar0 + 8 * st, EROWS * CH * 4);
-        tma_load_2d(smem_u32(ering + st * STAGE_FLOATS), &map, C.s0 - 4, (C.q0 - 4 + CH * k) - A.in_col0, bar0 + 8 * st);
+        tma_load_2d(ering + st * STAGE_BYTES, &map, C.s0 - 2, (C.q0 - 4 + CH * k) - A.in_col0, bar0 + 8 * st);
       }
     }
     // column masks of the first chunk (lane l holds column cbase + l - 8)
@@ -653,8 +696,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 1) k_chain_fused(const __g
       if (lane == 0 && kc + NST - 2 < nchunks) {
         const unsigned sn = (kbase + kc + NST - 2) % NST;
         mbar_expect_tx(bar0 + 8 * sn, EROWS * CH * 4);
-        tma_load_2d(smem_u32(ering + sn * STAGE_FLOATS), &map, C.s0 - 4, (C.q0 - 4 + CH * (kc + NST - 2)) - A.in_col0,
-                    bar0 + 8 * sn);
+        tma_load_2d(ering + sn * STAGE_BYTES, &map, C.s0 - 2, (C.q0 - 4 + CH * (kc + NST - 2)) - A.in_col0, bar0 + 8 * sn);
       }
       if constexpr (S::MASKS) {
         const int c = C.q0 - 4 + CH * (kc + 1) + lane - 8;
@@ -672,11 +714,11 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 1) k_chain_fused(const __g
           mjs[ph] = mjo[ph] = 0u;
         }
       }
-      march_step<S, 0>(C, L, t0 + 0, st, kbase, mjs[0], mjo[0]);
-      march_step<S, 1>(C, L, t0 + 1, st, kbase, mjs[1], mjo[1]);
-      march_step<S, 2>(C, L, t0 + 2, st, kbase, mjs[2], mjo[2]);
-      march_step<S, 3>(C, L, t0 + 3, st, kbase, mjs[3], mjo[3]);
-      march_step<S, 4>(C, L, t0 + 4, st, kbase, mjs[4], mjo[4]);
+      march_step<S, 0>(C, L, t0 + 0, st, mjs[0], mjo[0]);
+      march_step<S, 1>(C, L, t0 + 1, st, mjs[1], mjo[1]);
+      march_step<S, 2>(C, L, t0 + 2, st, mjs[2], mjo[2]);
+      march_step<S, 3>(C, L, t0 + 3, st, mjs[3], mjo[3]);
+      march_step<S, 4>(C, L, t0 + 4, st, mjs[4], mjo[4]);
       cm_cur = cm_next;
     }
     kglob += nchunks;
@@ -831,6 +873,21 @@ bool fused_eligible(FusedState& st, const std::vector<double>& X, const std::vec
   return true;
 }
 
+void make_fixup_args(const FusedState& st, const SlabView& v, const ChainDev& p, FixupArgs* out) {
+  const WindowClass wn = classify(p.rn, v.res), w1 = classify(p.r1, v.res), w2 = classify(p.r2, v.res);
+  FixupArgs a{};
+  a.rows = v.rows; a.cols_total = v.cols_total; a.in_col0 = v.in_col0; a.in_ncols = v.in_ncols; a.out_col0 = v.out_col0;
+  for (int k = 0; k < 3; ++k) { a.wn[k] = wn.w[k]; a.w1[k] = w1.w[k]; a.w2[k] = w2.w[k]; }
+  a.tip1 = w1.tips_on_circle; a.tip2 = w2.tips_on_circle;
+  a.ncrit = p.ncrit;
+  a.n_full = (double)wn.n;
+  a.res = v.res; a.slope_crit = p.slope_crit; a.step_crit = p.step_crit; a.rough_crit = p.rough_crit;
+  a.fuse_w = p.fuse_w;
+  a.rowmask = (const unsigned char*)st.d_rowmask;
+  a.colmask = (const unsigned char*)st.d_colmask;
+  *out = a;
+}
+
 int launch_chain_fused(FusedState& st, const SlabView& v, const ChainDev& p, const float* elev, const ChainOut& o, unsigned* list,
                        unsigned* count, unsigned cap, int sms, cudaStream_t s) {
   if (st.shape_id < 0) { st.why = "fused stencil not eligible"; return 1; }
@@ -853,7 +910,7 @@ int launch_chain_fused(FusedState& st, const SlabView& v, const ChainDev& p, con
   FusedArgs a{};
   a.rows = v.rows; a.cols_total = v.cols_total;
   a.in_col0 = v.in_col0; a.in_ncols = v.in_ncols; a.out_col0 = v.out_col0; a.out_ncols = v.out_ncols;
-  a.nstrips = (v.rows + STRIP - 1) / STRIP;
+  a.nstrips = (v.rows + OROWS - 1) / OROWS;
   {
     const int total_warps = sms * WARPS_PER_CTA;
     const int nseg0 = std::max(1, (v.out_ncols + 199) / 200);
@@ -867,6 +924,14 @@ int launch_chain_fused(FusedState& st, const SlabView& v, const ChainDev& p, con
   }
   const double N = wn.n, K2 = wn.k2;
   a.a_cov = (float)(res * res * K2 / N);
+  a.half_a = 0.5f * a.a_cov;
+  // certification constants (DESIGN.md "certification"); env overrides exist for calibration runs only
+  double rough_k = 0.06, cond_k = 0.25;
+  if (const char* e = std::getenv("TE_FUSED_ROUGH_K")) rough_k = std::atof(e);
+  if (const char* e = std::getenv("TE_FUSED_COND_K")) cond_k = std::atof(e);
+  a.stats = std::getenv("TE_FUSED_STATS") != nullptr;
+  a.cond_k = (float)cond_k;
+  a.rough_thr = (float)((rough_k / p.rough_crit) * (rough_k / p.rough_crit) * (N - 1.0) / N);
   a.kp = (float)(-res / N);
   a.invN = (float)(1.0 / N);
   a.n_over_nm1 = (float)(N / (N - 1.0));
@@ -875,6 +940,20 @@ int launch_chain_fused(FusedState& st, const SlabView& v, const ChainDev& p, con
   a.inv_ncrit = (float)(1.0 / (double)p.ncrit);
   a.rough_crit = (float)p.rough_crit; a.inv_rough_crit = (float)(1.0 / p.rough_crit);
   a.fuse_w = p.fuse_w;
+  auto B2 = [](double v) {
+    const float f = (float)v;
+    unsigned u;
+    std::memcpy(&u, &f, 4);
+    return ((unsigned long long)u << 32) | (unsigned long long)u;
+  };
+  a.k_invN = B2(1.0 / N); a.k_minvN = B2(-1.0 / N); a.k_kp = B2(-res / N); a.k_half_a = B2(0.5 * (double)a.a_cov);
+  a.k_nnm1 = B2(N / (N - 1.0)); a.k_rough_thr = B2((double)a.rough_thr);
+  a.k_minv_slope = B2(-1.0 / p.slope_crit); a.k_minv_rough = B2(-1.0 / p.rough_crit);
+  a.k_m0 = B2(wn.w[2] >= 0 ? 2 * wn.w[2] + 1 : 0); a.k_m1 = B2(wn.w[1] >= 0 ? 2 * wn.w[1] + 1 : 0);
+  a.k_one = B2(1.0); a.k_mone = B2(-1.0); a.k_two = B2(2.0); a.k_half = B2(0.5); a.k_mhalf = B2(-0.5); a.k_1p5 = B2(1.5);
+  a.k_0375 = B2(0.375); a.k_m03125 = B2(-0.3125);
+  a.k_p0 = B2(0.16666752099990845); a.k_p1 = B2(0.07495298236608505); a.k_p2 = B2(0.045470330864191055);
+  a.k_p3 = B2(0.024179592728614807); a.k_p4 = B2(0.0421663373708725);
   a.rowmask = (const unsigned char*)st.d_rowmask;
   a.colmask = (const unsigned char*)st.d_colmask;
   a.slope = o.slope; a.step = o.step; a.rough = o.rough; a.trav = o.trav;

@@ -25,6 +25,24 @@ struct FusedState {
 bool fused_eligible(FusedState& st, const std::vector<double>& X, const std::vector<double>& Y, const te_geometry* g,
                     const te_chain_params* p);
 
+// Arguments of the tier-2 fix-up kernel (te_fixup.cu): integer window description + parameters.
+struct FixupArgs {
+  int rows, cols_total, in_col0, in_ncols, out_col0;
+  int wn[3], w1[3], w2[3];  // half-width per |column offset| (-1: column not in the window)
+  int tip1, tip2;           // (+-2,0),(0,+-2) decided by the mask tables
+  int ncrit;
+  double n_full;            // cells of the full normals window
+  double res, slope_crit, step_crit, rough_crit;
+  float fuse_w;
+  const unsigned char* rowmask;
+  const unsigned char* colmask;
+};
+
+// Fills the tier-2 arguments for the shape the fused stencil was found eligible for.
+void make_fixup_args(const FusedState& st, const SlabView& v, const ChainDev& p, FixupArgs* out);
+void launch_fixup_t2(const FixupArgs& a, const float* elev, const ChainOut& o, const unsigned* list, const unsigned* count,
+                     unsigned cap, unsigned* list3, unsigned* count3, int sms, cudaStream_t s);
+
 // Returns 0 on success.  Cells whose result could not be certified in fp32 are appended to `list`.
 int launch_chain_fused(FusedState& st, const SlabView& v, const ChainDev& p, const float* elev, const ChainOut& o, unsigned* list,
                        unsigned* count, unsigned cap, int sms, cudaStream_t s);
