@@ -1,4 +1,336 @@
-// placeholder, replaced below
+/*
+ * te_oracle_footprint.cpp — CPU ORACLE of the circular footprint sweep (test infrastructure, NOT product code).
+ *
+ * Restates TraversabilityMap::traversabilityFootprint(radius, offset)
+ *   traversability_estimation/src/TraversabilityMap.cpp:307-318
+ * and everything it reaches: isTraversable(center, radiusMax, ..., radiusMin) :654-746,
+ * isTraversableForFilters :774-792, checkForStep :794-865, checkForSlope :867-893, together with the
+ * grid_map_core pieces those lines call (SpiralIterator, CircleIterator, LineIterator, getSubmap,
+ * getIndex, isInside — SURVEY.md Appendix A.1-A.3, recalled from ros-noetic-grid-map 1.6.x).
+ *
+ * PARITY UNPINNED: the reference's fixture holds NaN in all three footprint layers, so nothing in
+ * the reference pins this code; the decisions taken are listed in oracle/README.md.
+ * All geometry is literal IEEE double in the operand order written (build with -ffp-contract=off).
+ */
 #include "te_oracle.h"
-extern "C" int teo_footprint(const teo_geometry*, const teo_footprint_params*, const float*, const float*, const float*, const float*, float*, float*, float*, int) { return 99; }
-extern "C" int teo_spiral_offsets(double, double, int32_t*, int32_t*, int) { return -1; }
+
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <limits>
+#include <vector>
+
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+namespace {
+
+constexpr float kNaNf = std::numeric_limits<float>::quiet_NaN();
+
+struct V2 {
+  double x, y;
+};
+inline V2 operator+(V2 a, V2 b) { return {a.x + b.x, a.y + b.y}; }
+inline V2 operator-(V2 a, V2 b) { return {a.x - b.x, a.y - b.y}; }
+inline double norm(V2 a) { return std::sqrt(a.x * a.x + a.y * a.y); }
+inline double dot(V2 a, V2 b) { return a.x * b.x + a.y * b.y; }
+
+struct Map {
+  int rows, cols;
+  double res;
+  V2 len, pos;
+  const float* trav;
+  const float* slope;
+  const float* step;
+  const float* elev;
+  std::vector<double> X, Y;
+  float at(const float* l, int i, int j) const { return l[(size_t)j * rows + i]; }
+};
+
+inline double cell_coord(double map_pos, double length, double res, int idx) {
+  const double offset = 0.5 * length - 0.5 * res;
+  return (map_pos + offset) + res * (-(double)idx);
+}
+
+// grid_map::checkIfPositionWithinMap (A.1): half-open box test in the flipped frame.
+inline bool is_inside(const Map& m, V2 p) {
+  const double tx = -((p.x - m.pos.x) - 0.5 * m.len.x);
+  const double ty = -((p.y - m.pos.y) - 0.5 * m.len.y);
+  return tx >= 0.0 && ty >= 0.0 && tx < m.len.x && ty < m.len.y;
+}
+
+// grid_map::getIndexFromPosition (A.1): truncation of -(position - 0.5*length - mapPosition)/resolution.
+inline bool get_index(const Map& m, V2 p, int& i, int& j) {
+  const double vx = ((p.x - 0.5 * m.len.x) - m.pos.x) / m.res;
+  const double vy = ((p.y - 0.5 * m.len.y) - m.pos.y) / m.res;
+  i = (int)(-vx);
+  j = (int)(-vy);
+  return is_inside(m, p) && i >= 0 && j >= 0 && i < m.rows && j < m.cols;
+}
+
+// grid_map::boundPositionToRange (A.2).
+inline void bound_position(const Map& m, V2& p) {
+  double sh[2] = {(p.x - m.pos.x) + 0.5 * m.len.x, (p.y - m.pos.y) + 0.5 * m.len.y};
+  const double pp[2] = {p.x, p.y};
+  const double ln[2] = {m.len.x, m.len.y};
+  for (int k = 0; k < 2; ++k) {
+    double eps = 10.0 * std::numeric_limits<double>::epsilon();
+    if (std::fabs(pp[k]) > 1.0) eps *= std::fabs(pp[k]);
+    if (sh[k] <= 0.0) { sh[k] = eps; continue; }
+    if (sh[k] >= ln[k]) { sh[k] = ln[k] - eps; continue; }
+  }
+  p.x = (sh[0] + m.pos.x) - 0.5 * m.len.x;
+  p.y = (sh[1] + m.pos.y) - 0.5 * m.len.y;
+}
+
+template <class F>
+inline void for_circle(const Map& m, int i, int j, double radius, F&& f) {
+  const int R = (int)std::floor(radius / m.res) + 1;
+  const double r2 = radius * radius;
+  const int a0 = std::max(0, i - R), a1 = std::min(m.rows - 1, i + R);
+  const int b0 = std::max(0, j - R), b1 = std::min(m.cols - 1, j + R);
+  for (int a = a0; a <= a1; ++a) {
+    const double dx = m.X[a] - m.X[i];
+    for (int b = b0; b <= b1; ++b) {
+      const double dy = m.Y[b] - m.Y[j];
+      if (dx * dx + dy * dy <= r2) f(a, b);
+    }
+  }
+}
+
+// TraversabilityMap::checkForSlope, TraversabilityMap.cpp:867-893 (memoisation removed: pure function).
+bool check_slope(const Map& m, const teo_footprint_params& p, int i, int j) {
+  if (!(m.at(m.slope, i, j) == 0.0)) return true;                                    // :869
+  const double windowRadius = 3.0 * m.res;                                            // :871
+  const double criticalLength = p.max_gap_width / 3.0;                                // :872
+  const int nSlopesCritical = (int)std::floor(2 * windowRadius * criticalLength / std::pow(m.res, 2));  // :873
+  int nSlopes = 0;
+  bool ok = true;
+  for_circle(m, i, j, windowRadius, [&](int a, int b) {
+    if (m.at(m.slope, a, b) == 0.0) ++nSlopes;                                        // :881
+    if (nSlopes > nSlopesCritical) ok = false;                                        // :882-885
+  });
+  return ok;
+}
+
+// grid_map::LineIterator (Bresenham, A.1 family): cells from (i0,j0) to (i1,j1) inclusive.
+template <class F>
+inline void for_line(int i0, int j0, int i1, int j1, F&& f) {
+  const int dx = std::abs(i1 - i0), dy = std::abs(j1 - j0);
+  int inc1x = (i1 >= i0) ? 1 : -1, inc2x = inc1x;
+  int inc1y = (j1 >= j0) ? 1 : -1, inc2y = inc1y;
+  int den, num, numAdd, nCells;
+  if (dx >= dy) { inc1x = 0; inc2y = 0; den = dx; num = dx / 2; numAdd = dy; nCells = dx + 1; }
+  else { inc2x = 0; inc1y = 0; den = dy; num = dy / 2; numAdd = dx; nCells = dy + 1; }
+  int i = i0, j = j0;
+  for (int c = 0; c < nCells; ++c) {
+    if (!f(i, j)) return;
+    num += numAdd;
+    if (num >= den) { num -= den; i += inc1x; j += inc1y; }
+    i += inc2x; j += inc2y;
+  }
+}
+
+// TraversabilityMap::checkForStep, TraversabilityMap.cpp:794-865 (memoisation removed).
+bool check_step(const Map& m, const teo_footprint_params& p, int i, int j) {
+  if (!(m.at(m.step, i, j) == 0.0)) return true;                                      // :796
+  const double crit = p.critical_step_height;
+  const double windowRadiusStep = 2.5 * m.res;                                        // :798
+  const V2 center{m.X[i], m.Y[j]};
+  double height = (double)m.at(m.elev, i, j);                                         // :803
+  std::vector<std::pair<int, int>> indices;
+  for_circle(m, i, j, windowRadiusStep, [&](int a, int b) {
+    if ((double)m.at(m.elev, a, b) > crit + height && m.at(m.step, a, b) == 0.0) indices.emplace_back(a, b);  // :806-808
+  });
+  if (indices.empty()) indices.emplace_back(i, j);                                    // :810
+  for (const auto& idx : indices) {
+    const int a = idx.first, b = idx.second;
+    const V2 subLen{2.5 * m.res, 2.5 * m.res};                                       // :812
+    const V2 subMapPos{m.X[a], m.Y[b]};                                               // :815
+    const V2 toCenter = center - subMapPos;                                           // :816
+    // GridMap::getSubmap -> getSubmapInformation (A.1)
+    V2 tl{subMapPos.x + 0.5 * subLen.x, subMapPos.y + 0.5 * subLen.y};
+    bound_position(m, tl);
+    int ti, tj, bi, bj;
+    if (!get_index(m, tl, ti, tj)) return false;                                      // :818-822 (isSuccess false)
+    V2 br{subMapPos.x - 0.5 * subLen.x, subMapPos.y - 0.5 * subLen.y};
+    bound_position(m, br);
+    if (!get_index(m, br, bi, bj)) return false;
+    const V2 topLeftCorner{m.X[ti] + 0.5 * m.res, m.Y[tj] + 0.5 * m.res};
+    const int srows = bi - ti + 1, scols = bj - tj + 1;
+    const V2 subLength{(double)srows * m.res, (double)scols * m.res};
+    const V2 subPosition{topLeftCorner.x - 0.5 * subLength.x, topLeftCorner.y - 0.5 * subLength.y};
+    height = (double)m.at(m.elev, a, b);                                              // :823
+    for (int k = 0; k < srows * scols; ++k) {                                         // GridMapIterator over the submap (:824)
+      const int si = k % srows, sj = k / srows;
+      const int pi = ti + si, pj = tj + sj;
+      if (!(m.at(m.step, pi, pj) == 0.0 && (double)m.at(m.elev, pi, pj) < height - crit)) continue;  // :825
+      V2 pos{cell_coord(subPosition.x, subLength.x, m.res, si), cell_coord(subPosition.y, subLength.y, m.res, sj)};  // :827
+      const V2 vec = pos - subMapPos;                                                 // :828
+      if (norm(vec) < 0.025) continue;                                                // :829
+      if (norm(toCenter) > 0.025) {                                                   // :830
+        if (dot(toCenter, vec) < 0.0) continue;                                       // :831
+      }
+      pos = subMapPos + vec;                                                          // :833
+      while (norm((pos - subMapPos) + vec) < p.max_gap_width && is_inside(m, pos + vec)) pos = pos + vec;  // :834
+      int ei, ej;
+      get_index(m, pos, ei, ej);                                                      // :835-836
+      bool gapStart = false, gapEnd = false, fail = false;
+      for_line(a, b, ei, ej, [&](int li, int lj) {                                    // :839
+        if (li < 0 || lj < 0 || li >= m.rows || lj >= m.cols) return false;
+        const double e = (double)m.at(m.elev, li, lj);
+        if (e > height + crit) { fail = true; return false; }                         // :840-843
+        if (e < height - crit || !std::isfinite(m.at(m.elev, li, lj))) {              // :844-846
+          gapStart = true;
+        } else if (gapStart) {
+          gapEnd = true;                                                              // :847-850
+          return false;
+        }
+        return true;
+      });
+      if (fail) return false;
+      if (gapStart && !gapEnd) return false;                                          // :852-855
+    }
+  }
+  return true;                                                                        // :858
+}
+
+// grid_map::SpiralIterator visit order (A.3): ring 0 = centre; ring d generated by the walk that starts
+// at offset (d,0); rings are consumed back to front.  `edge` marks the rings that apply the circle test.
+struct SpiralOffsets {
+  std::vector<int> di, dj;
+  std::vector<unsigned char> edge;
+};
+
+inline int signum(int v) { return (0 < v) - (v < 0); }
+
+SpiralOffsets spiral_offsets(double radius, double res) {
+  SpiralOffsets s;
+  const int nRings = (int)std::ceil(radius / res);
+  s.di.push_back(0); s.dj.push_back(0); s.edge.push_back(0);
+  for (int d = 1; d <= nRings; ++d) {
+    std::vector<std::pair<int, int>> ring;
+    int px = d, py = 0;
+    do {
+      ring.emplace_back(px, py);
+      const int nx = -signum(py), ny = signum(px);
+      if (nx != 0 && (unsigned)std::sqrt((double)((px + nx) * (px + nx) + py * py)) == (unsigned)d) px += nx;
+      else if (ny != 0 && (unsigned)std::sqrt((double)(px * px + (py + ny) * (py + ny))) == (unsigned)d) py += ny;
+      else { px += nx; py += ny; }
+    } while (px != d || py != 0);
+    for (auto it = ring.rbegin(); it != ring.rend(); ++it) {
+      s.di.push_back(it->first);
+      s.dj.push_back(it->second);
+      s.edge.push_back((d == nRings || d == nRings - 1) ? 1 : 0);
+    }
+  }
+  return s;
+}
+
+}  // namespace
+
+extern "C" {
+
+int teo_spiral_offsets(double radius, double resolution, int32_t* di, int32_t* dj, int cap) {
+  if (!(radius >= 0.0) || !(resolution > 0.0)) return -1;
+  const SpiralOffsets s = spiral_offsets(radius, resolution);
+  // far from the border the circle test reduces to the exact lattice test (no position rounding)
+  int n = 0;
+  const double r2 = radius * radius;
+  for (size_t k = 0; k < s.di.size(); ++k) {
+    if (s.edge[k]) {
+      const double dx = resolution * (double)s.di[k], dy = resolution * (double)s.dj[k];
+      if (!(dx * dx + dy * dy <= r2)) continue;
+    }
+    if (n < cap) { di[n] = s.di[k]; dj[n] = s.dj[k]; }
+    ++n;
+  }
+  return n;
+}
+
+int teo_footprint(const teo_geometry* g, const teo_footprint_params* p, const float* trav, const float* slope, const float* step,
+                  const float* elev, float* out, float* slope_fp, float* step_fp, int nthreads) {
+  if (!g || g->rows <= 0 || g->cols <= 0 || !(g->resolution > 0.0) || !p || !trav || !slope || !step || !elev || !out) return 1;
+  Map m{g->rows, g->cols, g->resolution, {g->length_x, g->length_y}, {g->position_x, g->position_y}, trav, slope, step, elev, {}, {}};
+  m.X.resize(m.rows);
+  m.Y.resize(m.cols);
+  for (int i = 0; i < m.rows; ++i) m.X[i] = cell_coord(m.pos.x, m.len.x, m.res, i);
+  for (int j = 0; j < m.cols; ++j) m.Y[j] = cell_coord(m.pos.y, m.len.y, m.res, j);
+  int nt = 1;
+#ifdef _OPENMP
+  nt = nthreads > 0 ? nthreads : omp_get_max_threads();
+#else
+  (void)nthreads;
+#endif
+  (void)nt;
+  const size_t n = (size_t)m.rows * m.cols;
+  // isTraversableForFilters (:774-792) is a pure function of the layers: evaluate it once per cell.
+  std::vector<unsigned char> blocked(n);
+#pragma omp parallel for schedule(dynamic, 8) num_threads(nt)
+  for (int j = 0; j < m.cols; ++j)
+    for (int i = 0; i < m.rows; ++i) {
+      const size_t c = (size_t)j * m.rows + i;
+      const bool s_ok = check_slope(m, *p, i, j);
+      bool t_ok = true;
+      if (slope_fp) slope_fp[c] = (m.at(m.slope, i, j) == 0.0) ? (s_ok ? 1.0f : 0.0f) : kNaNf;  // :887,:883
+      if (step_fp) step_fp[c] = kNaNf;
+      if (s_ok) {                                                                      // short-circuit of :777-778
+        t_ok = check_step(m, *p, i, j);
+        if (step_fp && m.at(m.step, i, j) == 0.0) step_fp[c] = t_ok ? 1.0f : 0.0f;     // :859,:842,:854
+      }
+      blocked[c] = !(s_ok && t_ok);
+    }
+
+  const double radiusMin = p->radius;                         // :313  isTraversable(center, radius + offset, traversability, radius)
+  const double radiusMax = p->radius + p->offset;
+  const SpiralOffsets sp = spiral_offsets(radiusMax, m.res);
+  const double r2 = radiusMax * radiusMax;
+#pragma omp parallel for schedule(dynamic, 4) num_threads(nt)
+  for (int j = 0; j < m.cols; ++j)
+    for (int i = 0; i < m.rows; ++i) {
+      // isTraversable(center = getPosition(cell), radiusMax, false, ..., radiusMin), :654-746, branch :679-736
+      const double cx = m.X[i], cy = m.Y[j];
+      int nCells = 0;
+      double t = 0.0;
+      float result = kNaNf;
+      bool done = false;
+      for (size_t k = 0; k < sp.di.size() && !done; ++k) {
+        const int a = i + sp.di[k], b = j + sp.dj[k];
+        if (a < 0 || b < 0 || a >= m.rows || b >= m.cols) continue;                    // checkIfIndexInRange
+        if (sp.edge[k]) {                                                              // SpiralIterator::isInside on the last two rings
+          const double dx = m.X[a] - cx, dy = m.Y[b] - cy;
+          if (!(dx * dx + dy * dy <= r2)) continue;
+        }
+        const size_t c = (size_t)b * m.rows + a;
+        if (blocked[c]) {                                                              // :690
+          double uR;                                                                   // :691 getCurrentRadius()
+          const int ddi = sp.di[k], ddj = sp.dj[k];
+          if (p->radius_is_integer_norm) uR = (double)(int)std::sqrt((double)(ddi * ddi + ddj * ddj)) * m.res;
+          else uR = std::sqrt((double)(ddi * ddi + ddj * ddj)) * m.res;
+          if (radiusMin == 0.0) {
+            result = 0.0f;                                                             // :695
+          } else if (uR <= radiusMin) {
+            result = 0.0f;                                                             // :701
+          } else {
+            const double factor = ((uR - radiusMin) / (radiusMax - radiusMin) + 1.0) / 2.0;  // :706
+            t *= factor / nCells;                                                      // :707
+            result = (float)t;                                                         // :708
+          }
+          done = true;                                                                 // :714-717
+        } else {
+          ++nCells;                                                                    // :719
+          const float v = trav[c];
+          t += std::isfinite(v) ? (double)v : p->traversability_default;               // :720-724
+        }
+      }
+      if (!done) {
+        t /= nCells;                                                                   // :733
+        result = (float)t;                                                             // :734
+      }
+      out[(size_t)j * m.rows + i] = result;
+    }
+  return 0;
+}
+
+}  // extern "C"

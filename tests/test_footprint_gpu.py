@@ -1,0 +1,53 @@
+"""GPU parity of the circular footprint sweep (TraversabilityMap::traversabilityFootprint) against the oracle."""
+import numpy as np
+import pytest
+
+import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _same(a, b):
+    return np.array_equal(np.isnan(a), np.isnan(b)) and np.array_equal(a[~np.isnan(a)], b[~np.isnan(b)])
+
+
+def _run(te, ctx, oracle, g, og, layers, fp_t, fp_o):
+    t, s, st, e = (np.asfortranarray(x, dtype=np.float32) for x in layers)
+    ref, rs, rt = oracle.footprint(og, fp_o, t, s, st, e)
+    out = np.empty_like(t)
+    sfp = np.empty_like(t)
+    tfp = np.empty_like(t)
+    ctx.footprint(g, fp_t, t, s, st, e, out, te.MEM_HOST, slope_fp=sfp, step_fp=tfp)
+    return (out, sfp, tfp), (ref, rs, rt)
+
+
+def test_footprint_on_fixture_layers(te, ctx, oracle, fixture_map):
+    m, d = fixture_map
+    g = te.Geometry(m["rows"], m["cols"], m["resolution"], m["length_x"], m["length_y"], *m["position"], 0, 0)
+    og = oracle.Geometry(m["rows"], m["cols"], m["resolution"], m["length_x"], m["length_y"], *m["position"])
+    layers = (d["traversability"], d["traversability_slope"], d["traversability_step"], d["elevation"])
+    got, ref = _run(te, ctx, oracle, g, og, layers, te.FootprintParams.yaml_defaults(), oracle.FootprintParams.yaml_defaults())
+    for a, b, name in zip(got, ref, ("traversability_footprint", "slope_footprint", "step_footprint")):
+        assert _same(a, b), name
+    assert (ref[0] == 0).sum() > 100 and (ref[0] > 0).sum() > 100
+
+
+@pytest.mark.parametrize("case", [
+    dict(rows=160, cols=140, seed=21, res=0.02, offset=0.15),
+    dict(rows=160, cols=140, seed=22, res=0.02, offset=0.0),      # rMax = rMin = 0.3: 12 on-circle offsets
+    dict(rows=120, cols=133, seed=23, res=0.03, offset=0.15),
+    dict(rows=140, cols=120, seed=24, res=0.02, offset=0.15, position=(123.456, -78.9)),
+])
+def test_footprint_matches_oracle_on_chain_outputs(te, ctx, oracle, case):
+    res, pos = case["res"], case.get("position", (0.0, 0.0))
+    z = synth.terrain(case["rows"], case["cols"], res, case["seed"], "mixed", pos)
+    og = oracle.Geometry.make(case["rows"], case["cols"], res, pos)
+    g = te.Geometry.make(case["rows"], case["cols"], res, pos)
+    ch = oracle.chain(og, oracle.ChainParams.yaml_defaults(0), z)
+    fo, ft = oracle.FootprintParams.yaml_defaults(), te.FootprintParams.yaml_defaults()
+    fo.offset = ft.offset = case["offset"]
+    got, ref = _run(te, ctx, oracle, g, og, (ch["traversability"], ch["slope"], ch["step"], z), ft, fo)
+    for a, b, name in zip(got, ref, ("traversability_footprint", "slope_footprint", "step_footprint")):
+        assert _same(a, b), (name, int((np.isnan(a) != np.isnan(b)).sum()), float(np.nanmax(np.abs(a - b))))
+    assert (ref[0] == 0).any() and (ref[0] > 0).any()
+    assert np.isfinite(ref[2]).sum() > 0  # step == 0 cells exist, so the gap walk was exercised

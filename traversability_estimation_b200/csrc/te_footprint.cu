@@ -1,6 +1,296 @@
-// te_footprint.cu — footprint sweep (placeholder until the kernel lands).
+// te_footprint.cu — TraversabilityMap::traversabilityFootprint(radius, offset) as two kernels.
+//
+//   k_predicates   isTraversableForFilters (TraversabilityMap.cpp:774-792) for every cell of the slab
+//                  and its halo: checkForSlope (:867-893) and checkForStep (:794-865).  Both are pure
+//                  functions of the layers (their slope_footprint / step_footprint layers are only
+//                  memoisation), so they are evaluated once per cell instead of once per visit.  The
+//                  gap walk of checkForStep decides on absolute double positions (submap geometry,
+//                  dot products of perpendicular vectors, `norm < max_gap_width`), so this translation
+//                  unit is compiled with --fmad=false and replays the reference's operand order.
+//   k_sweep        isTraversable(center, radius + offset, ..., radius) (:654-746) for every cell:
+//                  walk the SpiralIterator visit order (table built on the host by executing the
+//                  iterator's own ring walk) until the first blocked cell.
+//
+// Layers are column-major float32; the slab/halo conventions are those of te_chain.
 #include "te_footprint.h"
+
+#include <cmath>
+#include <cstring>
+
 namespace te {
+namespace {
+
+struct Layers {
+  const float* __restrict__ trav;
+  const float* __restrict__ slope;
+  const float* __restrict__ step;
+  const float* __restrict__ elev;
+};
+
+struct FpArgs {
+  int rows, cols_total, in_col0, in_ncols, out_col0, out_ncols;
+  double res, lenx, leny, posx, posy;
+  const double* X;
+  const double* Y;
+  double rmin, rmax, rmax2, tdefault, maxgap, crit;
+  int int_norm;
+  int n_spiral;
+  const int* spiral;  // di & 0xff | (dj & 0xff) << 8 | edge << 16
+  int slope_R, step_R;
+};
+
+__device__ __forceinline__ float lay(const FpArgs& A, const float* l, int i, int j) {  // caller guarantees (i,j) is in the map
+  const int lb = j - A.in_col0;
+  if (lb < 0 || lb >= A.in_ncols) return nanf_();
+  return __ldg(l + (size_t)lb * A.rows + i);
+}
+
+__device__ __forceinline__ double cell_coord_d(double map_pos, double length, double res, int idx) {
+  const double offset = 0.5 * length - 0.5 * res;
+  return (map_pos + offset) + res * (-(double)idx);
+}
+
+__device__ __forceinline__ bool is_inside_d(const FpArgs& A, double px, double py) {
+  const double tx = -((px - A.posx) - 0.5 * A.lenx);
+  const double ty = -((py - A.posy) - 0.5 * A.leny);
+  return tx >= 0.0 && ty >= 0.0 && tx < A.lenx && ty < A.leny;
+}
+
+__device__ __forceinline__ bool get_index_d(const FpArgs& A, double px, double py, int& i, int& j) {
+  const double vx = ((px - 0.5 * A.lenx) - A.posx) / A.res;
+  const double vy = ((py - 0.5 * A.leny) - A.posy) / A.res;
+  i = (int)(-vx);
+  j = (int)(-vy);
+  return is_inside_d(A, px, py) && i >= 0 && j >= 0 && i < A.rows && j < A.cols_total;
+}
+
+__device__ __forceinline__ void bound_position_d(const FpArgs& A, double& px, double& py) {
+  double sx = (px - A.posx) + 0.5 * A.lenx, sy = (py - A.posy) + 0.5 * A.leny;
+  double ex = 10.0 * 2.220446049250313e-16, ey = ex;
+  if (fabs(px) > 1.0) ex *= fabs(px);
+  if (fabs(py) > 1.0) ey *= fabs(py);
+  if (sx <= 0.0) sx = ex; else if (sx >= A.lenx) sx = A.lenx - ex;
+  if (sy <= 0.0) sy = ey; else if (sy >= A.leny) sy = A.leny - ey;
+  px = (sx + A.posx) - 0.5 * A.lenx;
+  py = (sy + A.posy) - 0.5 * A.leny;
+}
+
+template <class F>
+__device__ __forceinline__ void for_circle_d(const FpArgs& A, int i, int j, double r2, int R, F&& f) {
+  const int a0 = max(0, i - R), a1 = min(A.rows - 1, i + R);
+  const int b0 = max(0, j - R), b1 = min(A.cols_total - 1, j + R);
+  const double cx = A.X[i], cy = A.Y[j];
+  for (int a = a0; a <= a1; ++a) {
+    const double dx = A.X[a] - cx;
+    for (int b = b0; b <= b1; ++b) {
+      const double dy = A.Y[b] - cy;
+      if (dx * dx + dy * dy <= r2) f(a, b);
+    }
+  }
+}
+
+// TraversabilityMap::checkForSlope, TraversabilityMap.cpp:867-893.
+__device__ bool check_slope_d(const FpArgs& A, const Layers& L, int i, int j) {
+  if (!(lay(A, L.slope, i, j) == 0.0f)) return true;
+  const double windowRadius = 3.0 * A.res;
+  const double criticalLength = A.maxgap / 3.0;
+  const int nCrit = (int)floor(2 * windowRadius * criticalLength / (A.res * A.res));
+  int n = 0;
+  for_circle_d(A, i, j, windowRadius * windowRadius, A.slope_R, [&](int a, int b) {
+    if (lay(A, L.slope, a, b) == 0.0f) ++n;
+  });
+  return !(n > nCrit);
+}
+
+// TraversabilityMap::checkForStep, TraversabilityMap.cpp:794-865.
+__device__ bool check_step_d(const FpArgs& A, const Layers& L, int i, int j) {
+  if (!(lay(A, L.step, i, j) == 0.0f)) return true;
+  const double crit = A.crit;
+  const double wr = 2.5 * A.res;
+  const double cx = A.X[i], cy = A.Y[j];
+  const double h0 = (double)lay(A, L.elev, i, j);
+  // candidate cells of the 2.5*res circle (at most 21): a bit per box cell, row index outer
+  const int R = A.step_R;
+  unsigned long long cand = 0ull;
+  {
+    const int a0 = max(0, i - R), a1 = min(A.rows - 1, i + R);
+    const int b0 = max(0, j - R), b1 = min(A.cols_total - 1, j + R);
+    for (int a = a0; a <= a1; ++a) {
+      const double dx = A.X[a] - cx;
+      for (int b = b0; b <= b1; ++b) {
+        const double dy = A.Y[b] - cy;
+        if (!(dx * dx + dy * dy <= wr * wr)) continue;
+        if ((double)lay(A, L.elev, a, b) > crit + h0 && lay(A, L.step, a, b) == 0.0f)
+          cand |= 1ull << ((a - (i - R)) * (2 * R + 1) + (b - (j - R)));
+      }
+    }
+  }
+  const bool self_only = cand == 0ull;
+  if (self_only) cand = 1ull << (R * (2 * R + 1) + R);
+  for (int bit = 0; bit < (2 * R + 1) * (2 * R + 1); ++bit) {
+    if (!((cand >> bit) & 1ull)) continue;
+    const int a = i - R + bit / (2 * R + 1), b = j - R + bit % (2 * R + 1);
+    const double sx = A.X[a], sy = A.Y[b];      // subMapPos
+    const double tcx = cx - sx, tcy = cy - sy;  // toCenter
+    const double half = 0.5 * (2.5 * A.res);
+    double tlx = sx + half, tly = sy + half;
+    bound_position_d(A, tlx, tly);
+    int ti, tj, bi, bj;
+    if (!get_index_d(A, tlx, tly, ti, tj)) return false;
+    double brx = sx - half, bry = sy - half;
+    bound_position_d(A, brx, bry);
+    if (!get_index_d(A, brx, bry, bi, bj)) return false;
+    const double cornx = A.X[ti] + 0.5 * A.res, corny = A.Y[tj] + 0.5 * A.res;
+    const int srows = bi - ti + 1, scols = bj - tj + 1;
+    const double slx = (double)srows * A.res, sly = (double)scols * A.res;
+    const double spx = cornx - 0.5 * slx, spy = corny - 0.5 * sly;
+    const double height = (double)lay(A, L.elev, a, b);
+    for (int k = 0; k < srows * scols; ++k) {
+      const int si = k % srows, sj = k / srows;
+      const int pi = ti + si, pj = tj + sj;
+      if (!(lay(A, L.step, pi, pj) == 0.0f && (double)lay(A, L.elev, pi, pj) < height - crit)) continue;
+      double px = cell_coord_d(spx, slx, A.res, si), py = cell_coord_d(spy, sly, A.res, sj);
+      const double vx = px - sx, vy = py - sy;
+      if (sqrt(vx * vx + vy * vy) < 0.025) continue;
+      if (sqrt(tcx * tcx + tcy * tcy) > 0.025) {
+        if (tcx * vx + tcy * vy < 0.0) continue;
+      }
+      px = sx + vx;
+      py = sy + vy;
+      for (;;) {
+        const double ex = (px - sx) + vx, ey = (py - sy) + vy;
+        if (!(sqrt(ex * ex + ey * ey) < A.maxgap && is_inside_d(A, px + vx, py + vy))) break;
+        px = px + vx;
+        py = py + vy;
+      }
+      int ei, ej;
+      get_index_d(A, px, py, ei, ej);
+      // LineIterator (Bresenham) from (a,b) to (ei,ej)
+      const int dx = abs(ei - a), dy = abs(ej - b);
+      int i1x = (ei >= a) ? 1 : -1, i2x = i1x, i1y = (ej >= b) ? 1 : -1, i2y = i1y;
+      int den, num, numAdd, nCells;
+      if (dx >= dy) { i1x = 0; i2y = 0; den = dx; num = dx / 2; numAdd = dy; nCells = dx + 1; }
+      else { i2x = 0; i1y = 0; den = dy; num = dy / 2; numAdd = dx; nCells = dy + 1; }
+      int li = a, lj = b;
+      bool gapStart = false, gapEnd = false;
+      for (int c = 0; c < nCells; ++c) {
+        if (li < 0 || lj < 0 || li >= A.rows || lj >= A.cols_total) break;
+        const float ef = lay(A, L.elev, li, lj);
+        const double e = (double)ef;
+        if (e > height + crit) return false;
+        if (e < height - crit || !finitef(ef)) {
+          gapStart = true;
+        } else if (gapStart) {
+          gapEnd = true;
+          break;
+        }
+        num += numAdd;
+        if (num >= den) { num -= den; li += i1x; lj += i1y; }
+        li += i2x; lj += i2y;
+      }
+      if (gapStart && !gapEnd) return false;
+    }
+  }
+  return true;
+}
+
+// blocked[] covers the whole input buffer (columns in_col0 .. in_col0+in_ncols).
+__global__ void __launch_bounds__(128) k_predicates(FpArgs A, Layers L, unsigned char* __restrict__ blocked, float* slope_fp, float* step_fp) {
+  const long long total = (long long)A.rows * A.in_ncols;
+  for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < total; c += (long long)gridDim.x * blockDim.x) {
+    const int i = (int)(c % A.rows);
+    const int j = A.in_col0 + (int)(c / A.rows);
+    const bool s_ok = check_slope_d(A, L, i, j);
+    bool t_ok = true;
+    float sfp = nanf_(), tfp = nanf_();
+    if (lay(A, L.slope, i, j) == 0.0f) sfp = s_ok ? 1.0f : 0.0f;
+    if (s_ok) {
+      t_ok = check_step_d(A, L, i, j);
+      if (lay(A, L.step, i, j) == 0.0f) tfp = t_ok ? 1.0f : 0.0f;
+    }
+    blocked[c] = (s_ok && t_ok) ? 0 : 1;
+    const int oj = j - A.out_col0;
+    if (oj >= 0 && oj < A.out_ncols) {
+      const size_t oc = (size_t)oj * A.rows + i;
+      if (slope_fp) slope_fp[oc] = sfp;
+      if (step_fp) step_fp[oc] = tfp;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) k_sweep(FpArgs A, Layers L, const unsigned char* __restrict__ blocked, float* __restrict__ out) {
+  const long long total = (long long)A.rows * A.out_ncols;
+  for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < total; c += (long long)gridDim.x * blockDim.x) {
+    const int i = (int)(c % A.rows);
+    const int j = A.out_col0 + (int)(c / A.rows);
+    const double cx = A.X[i], cy = A.Y[j];
+    int n = 0;
+    double t = 0.0;
+    float result = nanf_();
+    bool done = false;
+    for (int k = 0; k < A.n_spiral; ++k) {
+      const int w = __ldg(A.spiral + k);
+      const int di = (int)(signed char)(w & 0xff), dj = (int)(signed char)((w >> 8) & 0xff);
+      const int a = i + di, b = j + dj;
+      if (a < 0 || b < 0 || a >= A.rows || b >= A.cols_total) continue;
+      if (w & 0x10000) {
+        const double dx = A.X[a] - cx, dy = A.Y[b] - cy;
+        if (!(dx * dx + dy * dy <= A.rmax2)) continue;
+      }
+      const int lb = b - A.in_col0;
+      if (lb < 0 || lb >= A.in_ncols) continue;  // cannot happen with the halo te_footprint demands
+      const size_t cc = (size_t)lb * A.rows + a;
+      if (blocked[cc]) {
+        const int d2 = di * di + dj * dj;
+        const double nr = A.int_norm ? (double)(int)sqrt((double)d2) : sqrt((double)d2);
+        const double uR = nr * A.res;
+        if (A.rmin == 0.0 || uR <= A.rmin) {
+          result = 0.0f;
+        } else {
+          const double factor = ((uR - A.rmin) / (A.rmax - A.rmin) + 1.0) / 2.0;
+          t *= factor / (double)n;
+          result = (float)t;
+        }
+        done = true;
+        break;
+      }
+      ++n;
+      const float v = __ldg(L.trav + cc);
+      t += finitef(v) ? (double)v : A.tdefault;
+    }
+    if (!done) {
+      t /= (double)n;
+      result = (float)t;
+    }
+    out[c] = result;
+  }
+}
+
+inline int signum(int v) { return (0 < v) - (v < 0); }
+
+// grid_map::SpiralIterator::generateRing, executed literally.
+std::vector<int> build_spiral(double radius, double res) {
+  std::vector<int> s;
+  const int nRings = (int)std::ceil(radius / res);
+  s.push_back(0);
+  for (int d = 1; d <= nRings; ++d) {
+    std::vector<std::pair<int, int>> ring;
+    int px = d, py = 0;
+    do {
+      ring.emplace_back(px, py);
+      const int nx = -signum(py), ny = signum(px);
+      if (nx != 0 && (unsigned)std::sqrt((double)((px + nx) * (px + nx) + py * py)) == (unsigned)d) px += nx;
+      else if (ny != 0 && (unsigned)std::sqrt((double)(px * px + (py + ny) * (py + ny))) == (unsigned)d) py += ny;
+      else { px += nx; py += ny; }
+    } while (px != d || py != 0);
+    const int edge = (d == nRings || d == nRings - 1) ? 0x10000 : 0;
+    for (auto it = ring.rbegin(); it != ring.rend(); ++it) s.push_back((it->first & 0xff) | ((it->second & 0xff) << 8) | edge);
+  }
+  return s;
+}
+
+}  // namespace
+
 void FootprintState::release() {
   if (d_spiral) cudaFree(d_spiral);
   if (d_block) cudaFree(d_block);
@@ -8,11 +298,64 @@ void FootprintState::release() {
   spiral_cap = block_cap = 0;
   valid = false;
 }
-int footprint_halo(const te_geometry*, const te_footprint_params*) { return 0; }
-int launch_footprint(FootprintState& st, const SlabView&, const te_geometry*, const te_footprint_params*, const std::vector<double>&,
-                     const std::vector<double>&, const float*, const float*, const float*, const float*, float*, float*, float*, int,
-                     cudaStream_t, int*) {
-  st.why = "footprint sweep not built yet";
-  return TE_ERR_UNSUPPORTED;
+
+int footprint_halo(const te_geometry* g, const te_footprint_params* p) {
+  const double res = g->resolution;
+  const int spiral = (int)std::ceil((p->radius + p->offset) / res);
+  // predicates of a visited cell: slope window 3 cells; step: 2.5-cell circle + 3x3 submap + gap walk
+  const int walk = (int)std::ceil(p->max_gap_width / res) + 1;
+  return spiral + std::max(4, 3 + 1 + walk);
 }
+
+int launch_footprint(FootprintState& st, const SlabView& v, const te_geometry* g, const te_footprint_params* p,
+                     const std::vector<double>& X, const std::vector<double>& Y, const float* trav, const float* slope,
+                     const float* step, const float* elev, float* out, float* slope_fp, float* step_fp, int sms, cudaStream_t s,
+                     int* launches) {
+  (void)X; (void)Y;
+  const double rmax = p->radius + p->offset;
+  if (std::ceil(rmax / g->resolution) > 120.0) { st.why = "footprint radius exceeds 120 cells"; return TE_ERR_UNSUPPORTED; }
+  if (!st.valid || std::memcmp(&st.key_geo, g, sizeof(*g)) != 0 || std::memcmp(&st.key_par, p, sizeof(*p)) != 0) {
+    const std::vector<int> sp = build_spiral(rmax, g->resolution);
+    if (st.spiral_cap < sp.size() * sizeof(int)) {
+      if (st.d_spiral) cudaFree(st.d_spiral);
+      st.d_spiral = nullptr;
+      st.spiral_cap = 0;
+      if (cudaMalloc(&st.d_spiral, sp.size() * sizeof(int)) != cudaSuccess) { st.why = "cudaMalloc(spiral table) failed"; return TE_ERR_CUDA; }
+      st.spiral_cap = sp.size() * sizeof(int);
+    }
+    if (cudaMemcpyAsync(st.d_spiral, sp.data(), sp.size() * sizeof(int), cudaMemcpyHostToDevice, s) != cudaSuccess ||
+        cudaStreamSynchronize(s) != cudaSuccess) { st.why = "spiral table upload failed"; return TE_ERR_CUDA; }
+    st.n_spiral = (int)sp.size();
+    st.key_geo = *g;
+    st.key_par = *p;
+    st.valid = true;
+  }
+  const size_t ncell_in = (size_t)v.rows * v.in_ncols;
+  if (st.block_cap < ncell_in) {
+    if (st.d_block) cudaFree(st.d_block);
+    st.d_block = nullptr;
+    st.block_cap = 0;
+    if (cudaMalloc(&st.d_block, ncell_in) != cudaSuccess) { st.why = "cudaMalloc(predicate bytes) failed"; return TE_ERR_CUDA; }
+    st.block_cap = ncell_in;
+  }
+  FpArgs a{};
+  a.rows = v.rows; a.cols_total = v.cols_total; a.in_col0 = v.in_col0; a.in_ncols = v.in_ncols;
+  a.out_col0 = v.out_col0; a.out_ncols = v.out_ncols;
+  a.res = g->resolution; a.lenx = g->length_x; a.leny = g->length_y; a.posx = g->position_x; a.posy = g->position_y;
+  a.X = v.X; a.Y = v.Y;
+  a.rmin = p->radius; a.rmax = rmax; a.rmax2 = rmax * rmax; a.tdefault = p->traversability_default;
+  a.maxgap = p->max_gap_width; a.crit = p->critical_step_height; a.int_norm = p->radius_is_integer_norm;
+  a.n_spiral = st.n_spiral; a.spiral = (const int*)st.d_spiral;
+  a.slope_R = (int)std::floor(3.0 * g->resolution / g->resolution) + 1;
+  a.step_R = (int)std::floor(2.5 * g->resolution / g->resolution) + 1;
+  const Layers L{trav, slope, step, elev};
+  const long long t1 = (long long)ncell_in, t2 = (long long)v.rows * v.out_ncols;
+  const int g1 = (int)std::min<long long>((t1 + 127) / 128, (long long)sms * 16);
+  const int g2 = (int)std::min<long long>((t2 + 255) / 256, (long long)sms * 8);
+  k_predicates<<<std::max(g1, 1), 128, 0, s>>>(a, L, (unsigned char*)st.d_block, slope_fp, step_fp);
+  k_sweep<<<std::max(g2, 1), 256, 0, s>>>(a, L, (const unsigned char*)st.d_block, out);
+  if (launches) *launches = 2;
+  return 0;
+}
+
 }  // namespace te
