@@ -256,18 +256,11 @@ def main():
     elev[hl:hl + my_cols].copy_(own)
     outs = [torch.empty((my_cols, rows), dtype=torch.float32, device=dev) for _ in range(4)]
 
+    from traversability_estimation_b200.sharding import SlabPlan, exchange_halo
+    plan = SlabPlan(rank, world, cols_total, col0, my_cols, hl, hr)
+
     def exchange():
-        if world == 1:
-            return
-        ops = []
-        if rank > 0:
-            ops.append(dist.P2POp(dist.isend, elev[hl:hl + H], rank - 1))
-            ops.append(dist.P2POp(dist.irecv, elev[0:hl], rank - 1))
-        if rank < world - 1:
-            ops.append(dist.P2POp(dist.isend, elev[hl + my_cols - H:hl + my_cols], rank + 1))
-            ops.append(dist.P2POp(dist.irecv, elev[hl + my_cols:hl + my_cols + hr], rank + 1))
-        for w in dist.batch_isend_irecv(ops):
-            w.wait()
+        exchange_halo(dist, elev, plan, H)
 
     def step():
         exchange()

@@ -1,0 +1,72 @@
+"""The drop-in boundary without a GPU: the C-ABI library loads and exports what include/te_b200.h declares,
+fails loudly when no CUDA device exists, and the C++ plugin shells validate parameters like the reference."""
+import ctypes
+import os
+import re
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PLUGIN = os.path.join(ROOT, "traversability_estimation_b200", "plugin")
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "te_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    names = re.findall(r"\b(?:int|const char\*)\s+(te_[a-z0-9_]+)\s*\(", src)
+    assert len(names) >= 18
+    return names
+
+
+def test_library_exports_every_declared_symbol(te):
+    lib = te.load_library()
+    missing = [n for n in _declared() if not hasattr(lib, n)]
+    assert not missing, missing
+    assert lib.te_abi_version() == 1
+    assert set(te.capi.EXPORTS) <= set(_declared())
+
+
+def test_no_cpu_fallback(te):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(te.TEError) as e:
+        te.Context(0)
+    assert e.value.code == -3 and "no CPU fallback" in str(e.value)
+
+
+def test_argument_validation_messages(te):
+    lib = te.load_library()
+    lib.te_last_error.restype = ctypes.c_char_p
+    assert lib.te_create(None, 0) == -1
+    assert b"null" in lib.te_last_error()
+    assert lib.te_synchronize(None) == -1
+
+
+def _harness():
+    subprocess.check_call(["make", "-C", PLUGIN, "-s"])
+    return os.path.join(PLUGIN, "test_plugins")
+
+
+def test_plugin_configure_matches_reference_validation():
+    r = subprocess.run([_harness(), "configure"], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout.count("PASS") >= 16 and "FAIL" not in r.stdout
+    # the reference's own error strings (SlopeFilter.cpp:42, StepFilter.cpp:85)
+    assert "Critical slope must be in the interval [0, PI/2]" in r.stderr
+
+
+def test_plugin_update_fails_loudly_without_gpu():
+    r = subprocess.run([_harness(), "nogpu"], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "FAIL" not in r.stdout
+
+
+def test_manifest_names_the_reference_plugins():
+    xml = open(os.path.join(PLUGIN, "filter_plugins.xml")).read()
+    for n in ("SlopeFilter", "StepFilter", "RoughnessFilter"):
+        assert f'name="traversabilityFilters/{n}"' in xml
+        assert f'type="filters::{n}<grid_map::GridMap>"' in xml
+    assert xml.count('base_class_type="filters::FilterBase<grid_map::GridMap>"') == 4
+    assert 'path="lib/libtraversability_estimation_filters"' in xml

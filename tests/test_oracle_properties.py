@@ -1,0 +1,57 @@
+"""Oracle self-consistency on synthetic maps: documented edge semantics of the reference."""
+import numpy as np
+
+import synth
+
+
+def test_hole_semantics(oracle):
+    rows, cols = 64, 48
+    z = synth.fbm(rows, cols, 0.02, 3, 0.15)
+    z[20:26, 10:17] = np.nan
+    z[22, 13] = np.float32(0.05)  # isolated valid cell inside the hole: nPoints == 1 in the roughness window
+    z[40, 30] = np.inf
+    g = oracle.Geometry.make(rows, cols, 0.02)
+    o = oracle.chain(g, oracle.ChainParams.yaml_defaults(0), z, with_normals=True)
+    hole = ~np.isfinite(z)
+    for k in ("slope", "roughness", "traversability", "nx"):
+        assert np.isnan(o[k][hole]).all(), k          # no normal at invalid cells
+        assert np.isfinite(o[k][~hole]).all(), k
+    assert np.isfinite(o["step"][21, 11])             # the step layer is also written at invalid cells (StepFilter.cpp:147)
+    assert o["roughness"][22, 13] == 0.0              # 0/0 -> NaN -> comparison false -> 0.0 (RoughnessFilter.cpp:117-124)
+    assert o["nz"][22, 13] == 1.0 and o["slope"][22, 13] == 1.0
+
+
+def test_flat_and_tilted_planes(oracle):
+    rows, cols = 40, 40
+    g = oracle.Geometry.make(rows, cols, 0.02)
+    p = oracle.ChainParams.yaml_defaults(0)
+    flat = np.full((rows, cols), 0.25, np.float32)
+    o = oracle.chain(g, p, flat)
+    for k in ("slope", "step", "roughness", "traversability"):
+        assert (o[k] == 1.0).all(), k
+    # a plane with noise: slope equals the analytic inclination
+    X = synth.cell_positions(rows, 0.02)[:, None]
+    rng = np.random.default_rng(0)
+    z = (0.3 * X + 1e-4 * rng.standard_normal((rows, cols))).astype(np.float32)
+    o = oracle.chain(g, p, z, with_normals=True)
+    th = np.arccos(o["nz"][5:-5, 5:-5].astype(np.float64))
+    assert abs(np.median(th) - np.arctan(0.3)) < 2e-3
+    assert (o["nx"][5:-5, 5:-5] < 0).all()           # normal leans against +x for a surface rising with x
+
+
+def test_on_circle_membership_varies_with_position(oracle):
+    # r = 0.04 at 0.02 m: offsets (+-2,0),(0,+-2) sit exactly on the circle; CircleIterator decides them on
+    # absolute double positions, so the answer depends on the row
+    g = oracle.Geometry.make(2048, 8, 0.02)
+    counts = {len(oracle.circle_cells(g, i, 4, 0.04)[0]) for i in range(4, 2040, 7)}
+    assert len(counts) > 1 and counts <= {9, 10, 11, 12, 13}
+    g3 = oracle.Geometry.make(64, 64, 0.03)
+    assert len(oracle.circle_cells(g3, 30, 30, 0.05)[0]) == 9
+    assert len(oracle.circle_cells(g3, 0, 0, 0.05)[0]) == 4       # clipped at the map corner
+
+
+def test_check_for_slope_threshold(oracle):
+    # floor(2*(3*res)*(0.3/3)/res^2) = 29 at 0.02 m (the double expression is 29.999...), 20 at 0.03 m
+    import math
+    assert math.floor(2 * (3 * 0.02) * (0.3 / 3.0) / 0.02 ** 2) == 29
+    assert math.floor(2 * (3 * 0.03) * (0.3 / 3.0) / 0.03 ** 2) == 20

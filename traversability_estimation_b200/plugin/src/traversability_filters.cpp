@@ -1,0 +1,344 @@
+// traversability_filters.cpp — see include/traversability_estimation_b200/traversability_filters.hpp
+#include "traversability_estimation_b200/traversability_filters.hpp"
+
+#include <cmath>
+#include <limits>
+
+#if __has_include(<ros/console.h>)
+#include <ros/console.h>
+#endif
+#include <pluginlib/class_list_macros.h>
+
+#include "te_b200.h"
+
+namespace te_plugin {
+
+Device::Device() {}
+Device::~Device() {
+  if (ctx_) te_destroy(ctx_);
+}
+te_ctx* Device::get() {
+  if (!ctx_ && !failed_) {
+    if (te_create(&ctx_, 0) != TE_OK) {
+      ROS_ERROR("libte_b200: %s", te_last_error());
+      failed_ = true;
+      ctx_ = nullptr;
+    }
+  }
+  return ctx_;
+}
+
+namespace {
+
+te_geometry geometry_of(const grid_map::GridMap& m) {
+  te_geometry g;
+  g.rows = m.getSize()(0);
+  g.cols = m.getSize()(1);
+  g.resolution = m.getResolution();
+  g.length_x = m.getLength()(0);
+  g.length_y = m.getLength()(1);
+  g.position_x = m.getPosition()(0);
+  g.position_y = m.getPosition()(1);
+  g.start_row = m.getStartIndex()(0);
+  g.start_col = m.getStartIndex()(1);
+  return g;
+}
+
+// The kernels want the default start index.  For a circular-buffer map compute on an unwrapped copy
+// and scatter the new layers back into the buffer order of `out`.
+struct Unwrapped {
+  const grid_map::GridMap* in;
+  grid_map::GridMap copy;
+  bool wrapped;
+  explicit Unwrapped(const grid_map::GridMap& m) : in(&m), wrapped(m.getStartIndex()(0) != 0 || m.getStartIndex()(1) != 0) {
+    if (wrapped) {
+      copy = m;
+      copy.convertToDefaultStartIndex();
+    }
+  }
+  const grid_map::GridMap& map() const { return wrapped ? copy : *in; }
+};
+
+void scatter_back(const grid_map::GridMap& like, const float* unwrapped, float* dst) {
+  const int rows = like.getSize()(0), cols = like.getSize()(1);
+  const int s0 = like.getStartIndex()(0), s1 = like.getStartIndex()(1);
+  for (int j = 0; j < cols; ++j)
+    for (int i = 0; i < rows; ++i) dst[(size_t)((j + s1) % cols) * rows + (i + s0) % rows] = unwrapped[(size_t)j * rows + i];
+}
+
+te_chain_params yaml_defaults() {
+  te_chain_params p{};
+  p.normals_radius = 0.05;
+  p.normals_algorithm = TE_NORMALS_FIXTURE;
+  p.normals_positive_axis = 2;
+  p.slope_critical = 1.0;
+  p.step_critical = 0.12;
+  p.step_first_radius = 0.04;
+  p.step_second_radius = 0.04;
+  p.step_critical_cells = 4;
+  p.roughness_critical = 0.05;
+  p.roughness_radius = 0.05;
+  p.fuse_weight = 1.0f / 3.0f;
+  return p;
+}
+
+}  // namespace
+}  // namespace te_plugin
+
+namespace filters {
+
+using te_plugin::geometry_of;
+
+// ------------------------------------------------------------------ SlopeFilter
+template <typename T>
+SlopeFilter<T>::SlopeFilter() : criticalValue_(M_PI_4), type_("traversability_slope") {}
+template <typename T>
+SlopeFilter<T>::~SlopeFilter() {}
+
+template <typename T>
+bool SlopeFilter<T>::configure() {
+  if (!FilterBase<T>::getParam(std::string("critical_value"), criticalValue_)) {
+    ROS_ERROR("SlopeFilter did not find param critical_value");
+    return false;
+  }
+  if (criticalValue_ > M_PI_2 || criticalValue_ < 0.0) {
+    ROS_ERROR("Critical slope must be in the interval [0, PI/2]");
+    return false;
+  }
+  if (!FilterBase<T>::getParam(std::string("map_type"), type_)) {
+    ROS_ERROR("SlopeFilter did not find param map_type");
+    return false;
+  }
+  return true;
+}
+
+template <typename T>
+bool SlopeFilter<T>::update(const T& mapIn, T& mapOut) {
+  mapOut = mapIn;
+  mapOut.add(type_);  // NaN everywhere; cells without a surface normal keep it
+  const te_plugin::Unwrapped u(mapOut);
+  const float* nz = u.map().get("surface_normal_z").data();  // throws std::out_of_range like GridMap::at
+  te_ctx* ctx = device_.get();
+  if (!ctx) return false;
+  const te_geometry g = geometry_of(u.map());
+  grid_map::Matrix tmp;
+  float* dst = mapOut.get(type_).data();
+  if (u.wrapped) { tmp = grid_map::Matrix(g.rows, g.cols, 0.f); dst = tmp.data(); }
+  if (te_slope(ctx, &g, criticalValue_, nz, dst, TE_MEM_HOST) != TE_OK) {
+    ROS_ERROR("SlopeFilter: %s", te_last_error());
+    return false;
+  }
+  if (u.wrapped) te_plugin::scatter_back(mapOut, tmp.data(), mapOut.get(type_).data());
+  return true;
+}
+
+// ------------------------------------------------------------------ StepFilter
+template <typename T>
+StepFilter<T>::StepFilter()
+    : criticalValue_(0.3), firstWindowRadius_(0.08), secondWindowRadius_(0.08), nCellCritical_(5), type_("traversability_step") {}
+template <typename T>
+StepFilter<T>::~StepFilter() {}
+
+template <typename T>
+bool StepFilter<T>::configure() {
+  if (!FilterBase<T>::getParam(std::string("critical_value"), criticalValue_)) {
+    ROS_ERROR("Step filter did not find param critical_value");
+    return false;
+  }
+  if (criticalValue_ < 0.0) {
+    ROS_ERROR("Critical step height must be greater than zero");
+    return false;
+  }
+  if (!FilterBase<T>::getParam(std::string("first_window_radius"), firstWindowRadius_)) {
+    ROS_ERROR("Step filter did not find param 'first_window_radius'");
+    return false;
+  }
+  if (firstWindowRadius_ < 0.0) {
+    ROS_ERROR("'first_window_radius' must be greater than zero");
+    return false;
+  }
+  if (!FilterBase<T>::getParam(std::string("second_window_radius"), secondWindowRadius_)) {
+    ROS_ERROR("Step filter did not find param 'second_window_radius'");
+    return false;
+  }
+  if (secondWindowRadius_ < 0.0) {
+    ROS_ERROR("'second_window_radius' must be greater than zero");
+    return false;
+  }
+  if (!FilterBase<T>::getParam(std::string("critical_cell_number"), nCellCritical_)) {
+    ROS_ERROR("Step filter did not find param 'critical_cell_number'");
+    return false;
+  }
+  if (nCellCritical_ <= 0) {
+    ROS_ERROR("'critical_cell_number' must be greater than zero");
+    return false;
+  }
+  if (!FilterBase<T>::getParam(std::string("map_type"), type_)) {
+    ROS_ERROR("Step filter did not find param map_type");
+    return false;
+  }
+  return true;
+}
+
+template <typename T>
+bool StepFilter<T>::update(const T& mapIn, T& mapOut) {
+  mapOut = mapIn;
+  mapOut.add(type_);
+  const te_plugin::Unwrapped u(mapOut);
+  const float* elevation = u.map().get("elevation").data();
+  te_ctx* ctx = device_.get();
+  if (!ctx) return false;
+  const te_geometry g = geometry_of(u.map());
+  te_chain_params p = te_plugin::yaml_defaults();
+  p.step_critical = criticalValue_;
+  p.step_first_radius = firstWindowRadius_;
+  p.step_second_radius = secondWindowRadius_;
+  p.step_critical_cells = nCellCritical_;
+  grid_map::Matrix tmp;
+  float* dst = mapOut.get(type_).data();
+  if (u.wrapped) { tmp = grid_map::Matrix(g.rows, g.cols, 0.f); dst = tmp.data(); }
+  if (te_step(ctx, &g, &p, elevation, dst, TE_MEM_HOST) != TE_OK) {  // the step_height layer never leaves the device
+    ROS_ERROR("StepFilter: %s", te_last_error());
+    return false;
+  }
+  if (u.wrapped) te_plugin::scatter_back(mapOut, tmp.data(), mapOut.get(type_).data());
+  return true;
+}
+
+// ------------------------------------------------------------------ RoughnessFilter
+template <typename T>
+RoughnessFilter<T>::RoughnessFilter() : criticalValue_(0.3), estimationRadius_(0.3), type_("traversability_roughness") {}
+template <typename T>
+RoughnessFilter<T>::~RoughnessFilter() {}
+
+template <typename T>
+bool RoughnessFilter<T>::configure() {
+  if (!FilterBase<T>::getParam(std::string("critical_value"), criticalValue_)) {
+    ROS_ERROR("RoughnessFilter did not find param critical_value");
+    return false;
+  }
+  if (criticalValue_ < 0.0) {
+    ROS_ERROR("Critical roughness must be greater than zero");
+    return false;
+  }
+  if (!FilterBase<T>::getParam(std::string("estimation_radius"), estimationRadius_)) {
+    ROS_ERROR("RoughnessFilter did not find param estimation_radius");
+    return false;
+  }
+  if (estimationRadius_ < 0.0) {
+    ROS_ERROR("Roughness estimation radius must be greater than zero");
+    return false;
+  }
+  if (!FilterBase<T>::getParam(std::string("map_type"), type_)) {
+    ROS_ERROR("RoughnessFilter did not find param map_type");
+    return false;
+  }
+  return true;
+}
+
+template <typename T>
+bool RoughnessFilter<T>::update(const T& mapIn, T& mapOut) {
+  mapOut = mapIn;
+  mapOut.add(type_);
+  const te_plugin::Unwrapped u(mapOut);
+  const float* nx = u.map().get("surface_normal_x").data();
+  const float* elevation = u.map().get("elevation").data();
+  const float* ny = u.map().get("surface_normal_y").data();
+  const float* nz = u.map().get("surface_normal_z").data();
+  te_ctx* ctx = device_.get();
+  if (!ctx) return false;
+  const te_geometry g = geometry_of(u.map());
+  te_chain_params p = te_plugin::yaml_defaults();
+  p.roughness_critical = criticalValue_;
+  p.roughness_radius = estimationRadius_;
+  grid_map::Matrix tmp;
+  float* dst = mapOut.get(type_).data();
+  if (u.wrapped) { tmp = grid_map::Matrix(g.rows, g.cols, 0.f); dst = tmp.data(); }
+  if (te_roughness(ctx, &g, &p, elevation, nx, ny, nz, dst, TE_MEM_HOST) != TE_OK) {
+    ROS_ERROR("RoughnessFilter: %s", te_last_error());
+    return false;
+  }
+  if (u.wrapped) te_plugin::scatter_back(mapOut, tmp.data(), mapOut.get(type_).data());
+  return true;
+}
+
+// ------------------------------------------------------------------ FusedTraversabilityFilter
+template <typename T>
+FusedTraversabilityFilter<T>::FusedTraversabilityFilter()
+    : normalsRadius_(0.05), slopeCritical_(1.0), stepCritical_(0.12), stepR1_(0.04), stepR2_(0.04), roughCritical_(0.05),
+      roughRadius_(0.05), stepCells_(4), keepNormals_(false) {}
+template <typename T>
+FusedTraversabilityFilter<T>::~FusedTraversabilityFilter() {}
+
+template <typename T>
+bool FusedTraversabilityFilter<T>::configure() {
+  FilterBase<T>::getParam(std::string("normals_radius"), normalsRadius_);
+  FilterBase<T>::getParam(std::string("slope_critical_value"), slopeCritical_);
+  FilterBase<T>::getParam(std::string("step_critical_value"), stepCritical_);
+  FilterBase<T>::getParam(std::string("step_first_window_radius"), stepR1_);
+  FilterBase<T>::getParam(std::string("step_second_window_radius"), stepR2_);
+  FilterBase<T>::getParam(std::string("step_critical_cell_number"), stepCells_);
+  FilterBase<T>::getParam(std::string("roughness_critical_value"), roughCritical_);
+  FilterBase<T>::getParam(std::string("roughness_estimation_radius"), roughRadius_);
+  int keep = 0;
+  if (FilterBase<T>::getParam(std::string("keep_surface_normals"), keep)) keepNormals_ = keep != 0;
+  if (slopeCritical_ > M_PI_2 || slopeCritical_ < 0.0) {
+    ROS_ERROR("Critical slope must be in the interval [0, PI/2]");
+    return false;
+  }
+  if (stepCritical_ < 0.0 || stepR1_ < 0.0 || stepR2_ < 0.0 || stepCells_ <= 0 || roughCritical_ < 0.0 || roughRadius_ < 0.0 ||
+      normalsRadius_ < 0.0) {
+    ROS_ERROR("FusedTraversabilityFilter: critical values and radii must not be negative, critical_cell_number must be positive");
+    return false;
+  }
+  return true;
+}
+
+template <typename T>
+bool FusedTraversabilityFilter<T>::update(const T& mapIn, T& mapOut) {
+  mapOut = mapIn;
+  static const char* kOut[4] = {"traversability_slope", "traversability_step", "traversability_roughness", "traversability"};
+  static const char* kNrm[3] = {"surface_normal_x", "surface_normal_y", "surface_normal_z"};
+  for (const char* l : kOut) mapOut.add(l);
+  if (keepNormals_)
+    for (const char* l : kNrm) mapOut.add(l);
+  const te_plugin::Unwrapped u(mapOut);
+  const float* elevation = u.map().get("elevation").data();
+  te_ctx* ctx = device_.get();
+  if (!ctx) return false;
+  const te_geometry g = geometry_of(u.map());
+  te_chain_params p = te_plugin::yaml_defaults();
+  p.normals_radius = normalsRadius_;
+  p.slope_critical = slopeCritical_;
+  p.step_critical = stepCritical_;
+  p.step_first_radius = stepR1_;
+  p.step_second_radius = stepR2_;
+  p.step_critical_cells = stepCells_;
+  p.roughness_critical = roughCritical_;
+  p.roughness_radius = roughRadius_;
+  grid_map::Matrix tmp[7];
+  float* dst[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  for (int k = 0; k < 4; ++k) dst[k] = mapOut.get(kOut[k]).data();
+  if (keepNormals_)
+    for (int k = 0; k < 3; ++k) dst[4 + k] = mapOut.get(kNrm[k]).data();
+  if (u.wrapped)
+    for (int k = 0; k < 7; ++k)
+      if (dst[k]) { tmp[k] = grid_map::Matrix(g.rows, g.cols, 0.f); dst[k] = tmp[k].data(); }
+  if (te_chain(ctx, &g, nullptr, &p, elevation, dst[0], dst[1], dst[2], dst[3], dst[4], dst[5], dst[6], TE_MEM_HOST) != TE_OK) {
+    ROS_ERROR("FusedTraversabilityFilter: %s", te_last_error());
+    return false;
+  }
+  if (u.wrapped) {
+    for (int k = 0; k < 4; ++k) te_plugin::scatter_back(mapOut, tmp[k].data(), mapOut.get(kOut[k]).data());
+    if (keepNormals_)
+      for (int k = 0; k < 3; ++k) te_plugin::scatter_back(mapOut, tmp[4 + k].data(), mapOut.get(kNrm[k]).data());
+  }
+  return true;
+}
+
+}  // namespace filters
+
+PLUGINLIB_EXPORT_CLASS(filters::SlopeFilter<grid_map::GridMap>, filters::FilterBase<grid_map::GridMap>)
+PLUGINLIB_EXPORT_CLASS(filters::StepFilter<grid_map::GridMap>, filters::FilterBase<grid_map::GridMap>)
+PLUGINLIB_EXPORT_CLASS(filters::RoughnessFilter<grid_map::GridMap>, filters::FilterBase<grid_map::GridMap>)
+PLUGINLIB_EXPORT_CLASS(filters::FusedTraversabilityFilter<grid_map::GridMap>, filters::FilterBase<grid_map::GridMap>)

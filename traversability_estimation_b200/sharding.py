@@ -1,0 +1,55 @@
+"""Column-slab tiling of one map over the ranks of a torch.distributed job (one process per GPU).
+
+The chain is a pure stencil of `elevation`, so a map larger than one GPU is split along the COLUMN
+index (the slow storage axis of the column-major layers: a slab is one contiguous block) and the
+only exchange step is a one-shot swap of `halo` boundary columns of `elevation` with the two
+neighbours (NCCL send/recv over NVLink; gloo in the CPU tests).  Intermediates are recomputed in
+the halo, outputs stay sharded.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+
+@dataclass(frozen=True)
+class SlabPlan:
+    rank: int
+    world: int
+    cols_total: int
+    col_begin: int
+    col_count: int
+    halo_left: int
+    halo_right: int
+
+    @property
+    def buffer_cols(self) -> int:
+        return self.halo_left + self.col_count + self.halo_right
+
+
+def plan_slab(cols_total: int, world: int, rank: int, halo: int) -> SlabPlan:
+    """Contiguous, near-equal column ranges; halos clipped at the map edges."""
+    if not (0 <= rank < world) or cols_total < world:
+        raise ValueError((cols_total, world, rank))
+    base, extra = divmod(cols_total, world)
+    begin = rank * base + min(rank, extra)
+    count = base + (1 if rank < extra else 0)
+    hl = min(halo, begin)
+    hr = min(halo, cols_total - (begin + count))
+    return SlabPlan(rank, world, cols_total, begin, count, hl, hr)
+
+
+def exchange_halo(dist, buf, plan: SlabPlan, halo: int):
+    """buf: tensor of shape (buffer_cols, rows) holding [left halo | owned columns | right halo]; fills both
+    halos from the neighbours' owned boundary columns.  All ranks must call it."""
+    if plan.world == 1:
+        return
+    hl, hr, n = plan.halo_left, plan.halo_right, plan.col_count
+    ops = []
+    if plan.rank > 0:
+        ops.append(dist.P2POp(dist.isend, buf[hl:hl + min(halo, n)], plan.rank - 1))
+        ops.append(dist.P2POp(dist.irecv, buf[0:hl], plan.rank - 1))
+    if plan.rank < plan.world - 1:
+        ops.append(dist.P2POp(dist.isend, buf[hl + n - min(halo, n):hl + n], plan.rank + 1))
+        ops.append(dist.P2POp(dist.irecv, buf[hl + n:hl + n + hr], plan.rank + 1))
+    for w in dist.batch_isend_irecv(ops):
+        w.wait()
