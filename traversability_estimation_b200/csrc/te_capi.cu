@@ -239,23 +239,20 @@ int run_chain_device(te_ctx* c, const te_geometry* g, const te_slab& s, const te
   }
   const size_t in_stride = (size_t)g->rows * v.in_ncols, out_stride = (size_t)g->rows * v.out_ncols;
   if (use_fused) {
-    const unsigned cap = (unsigned)std::min<size_t>(out_stride, (size_t)1 << 26);
+    const unsigned cap = (unsigned)std::min<size_t>(out_stride * (size_t)nmaps, (size_t)1 << 26);
     TE_CUDA(c->worklist.reserve(sizeof(unsigned) * (size_t)cap));
     TE_CUDA(c->worklist3.reserve(sizeof(unsigned) * (size_t)cap));
     TE_CUDA(c->counter.reserve(sizeof(unsigned) * 8));
-    for (int m = 0; m < nmaps; ++m) {
-      te::ChainOut om = o;
-      om.slope += m * out_stride; om.step += m * out_stride; om.rough += m * out_stride; om.trav += m * out_stride;
-      if (om.nx) om.nx += m * out_stride;
-      if (om.ny) om.ny += m * out_stride;
-      if (om.nz) om.nz += m * out_stride;
+    {  // one launch covers every map of the batch
+      const te::ChainOut& om = o;
+      const int m = 0;
       TE_CUDA(cudaMemsetAsync(c->counter.p, 0, sizeof(unsigned) * 8, c->stream));
       te_ctx::Ev3 ev{};
       if (c->timing) {
         TE_CUDA(cudaEventCreate(&ev.a)); TE_CUDA(cudaEventCreate(&ev.b)); TE_CUDA(cudaEventCreate(&ev.c));
         TE_CUDA(cudaEventRecord(ev.a, c->stream));
       }
-      int rc = te::launch_chain_fused(c->fused, v, d, elev + m * in_stride, om, (unsigned*)c->worklist.p,
+      int rc = te::launch_chain_fused(c->fused, v, d, nmaps, elev + m * in_stride, om, (unsigned*)c->worklist.p,
                                       (unsigned*)c->counter.p, cap, c->sms, c->stream);
       if (rc != 0) return fail(TE_ERR_CUDA, "fused chain launch failed: %s", c->fused.why.c_str());
       if (int r2 = launch_check(c, "k_chain_fused")) return r2;

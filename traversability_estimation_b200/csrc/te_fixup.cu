@@ -193,12 +193,13 @@ __global__ void __launch_bounds__(128) k_fixup_t2(FixupArgs A, const float* __re
                                                   unsigned cap, unsigned* list3, unsigned* count3) {
   unsigned n = *count;
   if (n > cap) n = cap;
-  const Elev E{elev, A.rows, A.in_col0, A.in_ncols, A.cols_total};
   for (unsigned k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
     const unsigned w = list[k];
     const unsigned c = w & 0x3fffffffu;
-    const int i = (int)(c % (unsigned)A.rows);
-    const int j = A.out_col0 + (int)(c / (unsigned)A.rows);
+    const unsigned mapi = c / A.map_cells, cl = c - mapi * A.map_cells;
+    const int i = (int)(cl % (unsigned)A.rows);
+    const int j = A.out_col0 + (int)(cl / (unsigned)A.rows);
+    const Elev E{elev + (size_t)mapi * A.in_map_stride, A.rows, A.in_col0, A.in_ncols, A.cols_total};
     const bool do_n = (w >> 30) & 1u, do_s = (w >> 31) & 1u;
     float s, r, t;
     bool escalate = false;

@@ -55,6 +55,8 @@ struct FusedArgs {
   int rows, cols_total;
   int in_col0, in_ncols, out_col0, out_ncols;
   int nstrips, nseg, seg_len;
+  int nmaps;                    // independent maps stored back to back (te_chain_batched); 1 otherwise
+  unsigned map_cells;           // rows * out_ncols: output cells per map
   float half_a;     // 0.5 * res^2 * K2 / N   (Cxx = Cyy of a full window is a = 2*half_a)
   float a_cov;
   float kp;         // -res / N         (Cxz = kp * sum k*w)
@@ -69,7 +71,7 @@ struct FusedArgs {
   int stats;        // 1: count[1..3] += cells flagged per cause (lambda0, conditioning, small-angle rounding)
   // constants pre-broadcast to both halves of a register pair (one LDC.64 each)
   f2 k_invN, k_minvN, k_kp, k_half_a, k_nnm1, k_rough_thr, k_minv_slope, k_minv_rough, k_m0, k_m1;
-  f2 k_one, k_mone, k_two, k_half, k_mhalf, k_1p5, k_0375, k_m03125, k_p0, k_p1, k_p2, k_p3, k_p4;
+  f2 k_one, k_mone, k_two, k_half, k_mhalf, k_1p5, k_0375, k_m03125, k_p0, k_p1, k_p2, k_p3, k_p4, k_p5, k_p6, k_p7;
   const unsigned char* rowmask;  // per global row: bit0/1 pass-1 tips (-2,0)/(+2,0); bit2/3 pass-2 tips
   const unsigned char* colmask;  // per global column, same bits for (0,-2)/(0,+2)
   float* slope;
@@ -190,10 +192,10 @@ __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
         : "memory");
   }
 }
-__device__ __forceinline__ void tma_load_2d(unsigned dst, const CUtensorMap* map, int c0, int c1, unsigned bar) {
+__device__ __forceinline__ void tma_load_3d(unsigned dst, const CUtensorMap* map, int c0, int c1, int c2, unsigned bar) {
   asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
-      "l"(map), "r"(c0), "r"(c1), "r"(bar)
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst),
+      "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
       : "memory");
 }
 
@@ -274,23 +276,19 @@ struct Normal2 {
   unsigned flag;  // bit0: row x, bit1: row y could not be certified
 };
 
-// acos on [0,1] for both rows: 2*asin(sqrt((1-x)/2)) above 0.5, pi/2 - asin(x) below; asin by a
-// degree-4 polynomial in y^2 on [0, 0.5] (max rel. error 7e-8, fitted offline).
+// acos on [0,1] for both rows: sqrt(1-x) * P7(x) (Abramowitz-Stegun 4.4.46 form, coefficients refitted for
+// relative error; float32 evaluation: max abs error 2.2e-7, max rel. error 1.7e-7).  Branch-free.
 __device__ __forceinline__ f2 acos2(const FusedArgs& A, f2 x) {
-  const f2 u = fma2(x, A.k_mhalf, A.k_half);
-  const f2 xx = mul2(x, x);
-  const float x0 = lo(x), x1 = hi(x);
-  const bool bx = x0 >= 0.5f, by = x1 >= 0.5f;
-  const f2 y2 = mk(bx ? lo(u) : lo(xx), by ? hi(u) : hi(xx));
-  const f2 y = mk(bx ? sqrt_a(lo(u)) : x0, by ? sqrt_a(hi(u)) : x1);
-  f2 p = fma2(y2, A.k_p4, A.k_p3);
-  p = fma2(p, y2, A.k_p2);
-  p = fma2(p, y2, A.k_p1);
-  p = fma2(p, y2, A.k_p0);
-  const f2 a = fma2(mul2(y, y2), p, y);
-  const f2 sc = mk(bx ? 2.0f : -1.0f, by ? 2.0f : -1.0f);
-  const f2 of = mk(bx ? 0.0f : 1.5707963267948966f, by ? 0.0f : 1.5707963267948966f);
-  return fma2(a, sc, of);
+  const f2 u = sub2(A.k_one, x);
+  const f2 sq = mk(sqrt_a(lo(u)), sqrt_a(hi(u)));
+  f2 p = fma2(x, A.k_p7, A.k_p6);
+  p = fma2(p, x, A.k_p5);
+  p = fma2(p, x, A.k_p4);
+  p = fma2(p, x, A.k_p3);
+  p = fma2(p, x, A.k_p2);
+  p = fma2(p, x, A.k_p1);
+  p = fma2(p, x, A.k_p0);
+  return mul2(sq, p);
 }
 
 // Closed-form smallest eigenpair of the scatter matrix [[a,0,p],[0,a,q],[p,q,c]] of a full disk
@@ -374,15 +372,11 @@ __device__ __forceinline__ Normal2 finish_normal2(const FusedArgs& A, f2 Sw, f2 
   // layer = x < crit ? 1 - x/crit : 0  ==  max(1 - x/crit, 0)
   const f2 sl = fma2(theta, A.k_minv_slope, A.k_one);
   const f2 ro = fma2(r, A.k_minv_rough, A.k_one);
-  // a hole (invalid centre) has no normal: slope and roughness stay NaN and nothing needs certifying
-  // (SlopeFilter.cpp:71, RoughnessFilter.cpp:84)
-  const float e0 = lo(ec), e1 = hi(ec);
-  const bool v0 = fabsf(e0) < 3.0e38f, v1 = fabsf(e1) < 3.0e38f;
-  const float qn = __int_as_float(0x7fc00000);
-  o.slope = mk(v0 ? fmaxf(lo(sl), 0.0f) : qn, v1 ? fmaxf(hi(sl), 0.0f) : qn);
-  o.rough = mk(v0 ? fmaxf(lo(ro), 0.0f) : qn, v1 ? fmaxf(hi(ro), 0.0f) : qn);
-  if (!v0) { flag &= ~0x3du; o.nx = mk(qn, hi(o.nx)); o.ny = mk(qn, hi(o.ny)); o.nz = mk(qn, hi(o.nz)); }
-  if (!v1) { flag &= ~0x3c2u; o.nx = mk(lo(o.nx), qn); o.ny = mk(lo(o.ny), qn); o.nz = mk(lo(o.nz), qn); }
+  // a hole (invalid centre: NaN, or Inf - Inf) has no normal: slope and roughness stay NaN
+  // (SlopeFilter.cpp:71, RoughnessFilter.cpp:84); such cells are flagged by the Sww test and tier 2 confirms the NaN
+  const f2 inval = sub2(ec, ec);
+  o.slope = add2(mk(fmaxf(lo(sl), 0.0f), fmaxf(hi(sl), 0.0f)), inval);
+  o.rough = add2(mk(fmaxf(lo(ro), 0.0f), fmaxf(hi(ro), 0.0f)), inval);
   o.flag = flag;
   return o;
 }
@@ -425,7 +419,8 @@ struct StepCtx {
   int lane;
   int s0;             // first row held by the warp (strip row 0 = output row -2)
   int q0, q1;         // output columns of the unit
-  unsigned rm0, rm1;  // row masks of the lane's two rows
+  f2 tipU1, tipD1;    // pass-1 row tips: +0.0 where the on-circle offset (-2,0)/(+2,0) belongs to the window, NaN where not
+  f2 tipU2, tipD2;    // same for pass 2
   bool out_ok;        // lane produces output rows (lanes 1..30 and inside the map)
   size_t oc;          // running output offset (column jo, lane's first row)
   size_t ocn;         // same for the normals stage (column jn)
@@ -462,6 +457,9 @@ __device__ __forceinline__ void march_step(StepCtx<S>& C, Lane<S>& L, int t, uns
   }
   {
     float cmn[2], cmx[2], pmn[2], pmx[2];
+    // excluded on-circle tips become NaN (x + NaN), included ones pass through (x + 0): both rows in one FADD2
+    f2 TU = 0ull, TD = 0ull;
+    if constexpr (S::TIP1) { TU = add2(ZM2, C.tipU1); TD = add2(ZP2, C.tipD1); }
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
       const float lo3 = min3n(z[r + 1], z[r + 2], z[r + 3]), hi3 = max3n(z[r + 1], z[r + 2], z[r + 3]);
@@ -473,9 +471,7 @@ __device__ __forceinline__ void march_step(StepCtx<S>& C, Lane<S>& L, int t, uns
         mn = min3n(mn, z[r], z[r + 4]);
         mx = max3n(mx, z[r], z[r + 4]);
       } else if constexpr (S::TIP1) {
-        const unsigned rm = r ? C.rm1 : C.rm0;
-        const float qn = __int_as_float(0x7fc00000);
-        const float tu = (rm & 1u) ? z[r] : qn, td = (rm & 2u) ? z[r + 4] : qn;
+        const float tu = r ? hi(TU) : lo(TU), td = r ? hi(TD) : lo(TD);
         mn = min3n(mn, tu, td);
         mx = max3n(mx, tu, td);
       }
@@ -490,6 +486,12 @@ __device__ __forceinline__ void march_step(StepCtx<S>& C, Lane<S>& L, int t, uns
   const unsigned shcol = C.sh_lane + (t & 1) * SHBUF_BYTES;
   {
     float shv[2];
+    f2 TL1 = L.e[S4], TR1 = L.e[S0];
+    if constexpr (S::TIP1) {
+      const float qn = __int_as_float(0x7fc00000);
+      TL1 = add2(TL1, bc((cm_js & 1u) ? 0.0f : qn));
+      TR1 = add2(TR1, bc((cm_js & 2u) ? 0.0f : qn));
+    }
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
       auto R = [&](f2 v) { return r ? hi(v) : lo(v); };
@@ -499,12 +501,7 @@ __device__ __forceinline__ void march_step(StepCtx<S>& C, Lane<S>& L, int t, uns
         mx = max3n(mx, R(L.c1mx[S1]), R(L.c1mx[S3]));
       }
       if constexpr (S::W12 == 0 || S::TIP1) {
-        float tl = R(L.e[S4]), tr = R(L.e[S0]);
-        if constexpr (S::TIP1) {
-          const float qn = __int_as_float(0x7fc00000);
-          tl = (cm_js & 1u) ? tl : qn;
-          tr = (cm_js & 2u) ? tr : qn;
-        }
+        const float tl = R(TL1), tr = R(TR1);
         mn = min3n(mn, tl, tr);
         mx = max3n(mx, tl, tr);
       }
@@ -517,9 +514,11 @@ __device__ __forceinline__ void march_step(StepCtx<S>& C, Lane<S>& L, int t, uns
   __syncwarp();
   float v[6], f[6];
   f2 V0;
+  f2 SU = 0ull, SD = 0ull;
   {
     const f2 VM2 = lds64(shcol), VP2 = lds64(shcol + 16);
     V0 = lds64(shcol + 8);
+    if constexpr (S::TIP2) { SU = add2(VM2, C.tipU2); SD = add2(VP2, C.tipD2); }
     v[0] = lo(VM2); v[1] = hi(VM2); v[2] = lo(V0); v[3] = hi(V0); v[4] = lo(VP2); v[5] = hi(VP2);
 #pragma unroll
     for (int k = 0; k < 6; ++k) f[k] = gtf(v[k], A.step_crit);
@@ -538,11 +537,9 @@ __device__ __forceinline__ void march_step(StepCtx<S>& C, Lane<S>& L, int t, uns
         mx = max3n(mx, v[r], v[r + 4]);
         cnt += f[r] + f[r + 4];
       } else if constexpr (S::TIP2) {
-        const unsigned rm = r ? C.rm1 : C.rm0;
-        const bool iu = rm & 4u, id = rm & 8u;
-        const float qn = __int_as_float(0x7fc00000);
-        mx = max3n(mx, iu ? v[r] : qn, id ? v[r + 4] : qn);
-        cnt += (iu ? f[r] : 0.f) + (id ? f[r + 4] : 0.f);
+        const float tu = r ? hi(SU) : lo(SU), td = r ? hi(SD) : lo(SD);
+        mx = max3n(mx, tu, td);
+        cnt += gtf(tu, A.step_crit) + gtf(td, A.step_crit);  // NaN > crit is false
       }
       pmx[r] = mx;
       pc[r] = cnt;
@@ -592,6 +589,12 @@ __device__ __forceinline__ void march_step(StepCtx<S>& C, Lane<S>& L, int t, uns
   {
     float outv[2];
     unsigned sflag = 0;
+    f2 TL2 = L.sh[S4], TR2 = L.sh[S0];
+    if constexpr (S::TIP2) {
+      const float qn = __int_as_float(0x7fc00000);
+      TL2 = add2(TL2, bc((cm_jo & 4u) ? 0.0f : qn));
+      TR2 = add2(TR2, bc((cm_jo & 8u) ? 0.0f : qn));
+    }
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
       auto R = [&](f2 x) { return r ? hi(x) : lo(x); };
@@ -602,15 +605,9 @@ __device__ __forceinline__ void march_step(StepCtx<S>& C, Lane<S>& L, int t, uns
         cnt += R(L.s3c[S1]) + R(L.s3c[S3]);
       }
       if constexpr (S::W22 == 0 || S::TIP2) {
-        const float tl = R(L.sh[S4]), tr = R(L.sh[S0]);
-        bool il = true, ir = true;
-        if constexpr (S::TIP2) {
-          il = cm_jo & 4u;
-          ir = cm_jo & 8u;
-        }
-        const float qn = __int_as_float(0x7fc00000);
-        mx = max3n(mx, il ? tl : qn, ir ? tr : qn);
-        cnt += (il ? gtf(tl, A.step_crit) : 0.f) + (ir ? gtf(tr, A.step_crit) : 0.f);
+        const float tl = R(TL2), tr = R(TR2);
+        mx = max3n(mx, tl, tr);
+        cnt += gtf(tl, A.step_crit) + gtf(tr, A.step_crit);
       }
       sflag |= (mx > 3.0e38f) ? (1u << r) : 0u;  // an infinite elevation reached the window: the slow path sorts it out
       const float stepMax = fmaxf(mx, 0.0f);
@@ -654,14 +651,16 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 1) k_chain_fused(const __g
 
   const int total_warps = gridDim.x * WARPS_PER_CTA;
   const int gwarp = blockIdx.x * WARPS_PER_CTA + warp;
-  const int nunits = A.nstrips * A.nseg;
+  const int units_per_map = A.nstrips * A.nseg;
+  const int nunits = units_per_map * A.nmaps;
   unsigned kglob = 0;  // chunks consumed so far by this warp (stage = kglob % NST, parity = (kglob / NST) & 1)
 
   Lane<S> L;
-  StepCtx<S> C{A, ering + lane * 8u, shbuf + lane * 8u, lane, 0, 0, 0, 0u, 0u, false, 0, 0};
+  StepCtx<S> C{A, ering + lane * 8u, shbuf + lane * 8u, lane, 0, 0, 0, 0ull, 0ull, 0ull, 0ull, false, 0, 0};
 
   for (int unit = gwarp; unit < nunits; unit += total_warps) {
-    const int strip = unit % A.nstrips, seg = unit / A.nstrips;
+    const int mapi = unit / units_per_map, um = unit - mapi * units_per_map;
+    const int strip = um % A.nstrips, seg = um / A.nstrips;
     C.s0 = strip * OROWS - 2;
     C.q0 = A.out_col0 + seg * A.seg_len;
     C.q1 = min(C.q0 + A.seg_len, A.out_col0 + A.out_ncols);
@@ -669,11 +668,16 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 1) k_chain_fused(const __g
     const int nchunks = (nsteps + CH - 1) / CH;
     const int row0 = C.s0 + 2 * lane;
     C.out_ok = lane >= 1 && lane <= 30 && row0 < A.rows;
-    C.oc = (size_t)(C.q0 - A.out_col0) * A.rows + row0;
+    C.oc = (size_t)mapi * A.map_cells + (size_t)(C.q0 - A.out_col0) * A.rows + row0;
     C.ocn = C.oc;
     if constexpr (S::MASKS) {
-      C.rm0 = (row0 >= 0 && row0 < A.rows) ? A.rowmask[row0] : 0u;
-      C.rm1 = (row0 + 1 >= 0 && row0 + 1 < A.rows) ? A.rowmask[row0 + 1] : 0u;
+      const unsigned rm0 = (row0 >= 0 && row0 < A.rows) ? A.rowmask[row0] : 0u;
+      const unsigned rm1 = (row0 + 1 >= 0 && row0 + 1 < A.rows) ? A.rowmask[row0 + 1] : 0u;
+      const float qn = __int_as_float(0x7fc00000);
+      C.tipU1 = mk((rm0 & 1u) ? 0.f : qn, (rm1 & 1u) ? 0.f : qn);
+      C.tipD1 = mk((rm0 & 2u) ? 0.f : qn, (rm1 & 2u) ? 0.f : qn);
+      C.tipU2 = mk((rm0 & 4u) ? 0.f : qn, (rm1 & 4u) ? 0.f : qn);
+      C.tipD2 = mk((rm0 & 8u) ? 0.f : qn, (rm1 & 8u) ? 0.f : qn);
     }
     __syncwarp();  // every lane is done with the previous unit's smem
     const unsigned kbase = kglob;
@@ -681,7 +685,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 1) k_chain_fused(const __g
       for (int k = 0; k < NST - 2 && k < nchunks; ++k) {
         const unsigned st = (kbase + k) % NST;
         mbar_expect_tx(bar0 + 8 * st, EROWS * CH * 4);
-        tma_load_2d(ering + st * STAGE_BYTES, &map, C.s0 - 2, (C.q0 - 4 + CH * k) - A.in_col0, bar0 + 8 * st);
+        tma_load_3d(ering + st * STAGE_BYTES, &map, C.s0 - 2, (C.q0 - 4 + CH * k) - A.in_col0, mapi, bar0 + 8 * st);
       }
     }
     // column masks of the first chunk (lane l holds column cbase + l - 8)
@@ -696,7 +700,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 1) k_chain_fused(const __g
       if (lane == 0 && kc + NST - 2 < nchunks) {
         const unsigned sn = (kbase + kc + NST - 2) % NST;
         mbar_expect_tx(bar0 + 8 * sn, EROWS * CH * 4);
-        tma_load_2d(ering + sn * STAGE_BYTES, &map, C.s0 - 2, (C.q0 - 4 + CH * (kc + NST - 2)) - A.in_col0, bar0 + 8 * sn);
+        tma_load_3d(ering + sn * STAGE_BYTES, &map, C.s0 - 2, (C.q0 - 4 + CH * (kc + NST - 2)) - A.in_col0, mapi, bar0 + 8 * sn);
       }
       if constexpr (S::MASKS) {
         const int c = C.q0 - 4 + CH * (kc + 1) + lane - 8;
@@ -797,7 +801,7 @@ int launch_shape(FusedState& st, const CUtensorMap& map, const FusedArgs& a, int
     }
     attr_set = true;
   }
-  const int nunits = a.nstrips * a.nseg;
+  const int nunits = a.nstrips * a.nseg * a.nmaps;
   int grid = std::min(sms, (nunits + WARPS_PER_CTA - 1) / WARPS_PER_CTA);
   if (grid < 1) grid = 1;
   k_chain_fused<S><<<grid, WARPS_PER_CTA * 32, smem, s>>>(map, a);
@@ -877,6 +881,8 @@ void make_fixup_args(const FusedState& st, const SlabView& v, const ChainDev& p,
   const WindowClass wn = classify(p.rn, v.res), w1 = classify(p.r1, v.res), w2 = classify(p.r2, v.res);
   FixupArgs a{};
   a.rows = v.rows; a.cols_total = v.cols_total; a.in_col0 = v.in_col0; a.in_ncols = v.in_ncols; a.out_col0 = v.out_col0;
+  a.map_cells = (unsigned)((size_t)v.rows * v.out_ncols);
+  a.in_map_stride = (size_t)v.rows * v.in_ncols;
   for (int k = 0; k < 3; ++k) { a.wn[k] = wn.w[k]; a.w1[k] = w1.w[k]; a.w2[k] = w2.w[k]; }
   a.tip1 = w1.tips_on_circle; a.tip2 = w2.tips_on_circle;
   a.ncrit = p.ncrit;
@@ -888,19 +894,19 @@ void make_fixup_args(const FusedState& st, const SlabView& v, const ChainDev& p,
   *out = a;
 }
 
-int launch_chain_fused(FusedState& st, const SlabView& v, const ChainDev& p, const float* elev, const ChainOut& o, unsigned* list,
-                       unsigned* count, unsigned cap, int sms, cudaStream_t s) {
+int launch_chain_fused(FusedState& st, const SlabView& v, const ChainDev& p, int nmaps, const float* elev, const ChainOut& o,
+                       unsigned* list, unsigned* count, unsigned cap, int sms, cudaStream_t s) {
   if (st.shape_id < 0) { st.why = "fused stencil not eligible"; return 1; }
   if ((reinterpret_cast<uintptr_t>(elev) & 15u) != 0) { st.why = "elevation pointer is not 16-byte aligned"; return 1; }
-  if ((size_t)v.rows * v.out_ncols >= ((size_t)1 << 30)) { st.why = "slab has 2^30 or more cells"; return 1; }
+  if ((size_t)v.rows * v.out_ncols * (size_t)nmaps >= ((size_t)1 << 30)) { st.why = "launch covers 2^30 or more cells"; return 1; }
   PFN_encodeTiled enc = get_encode();
   if (!enc) { st.why = "cuTensorMapEncodeTiled entry point unavailable"; return 1; }
   CUtensorMap map;
-  const cuuint64_t dims[2] = {(cuuint64_t)v.rows, (cuuint64_t)v.in_ncols};
-  const cuuint64_t strides[1] = {(cuuint64_t)v.rows * sizeof(float)};
-  const cuuint32_t box[2] = {(cuuint32_t)EROWS, (cuuint32_t)CH};
-  const cuuint32_t estr[2] = {1, 1};
-  const CUresult cr = enc(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(elev), dims, strides, box, estr,
+  const cuuint64_t dims[3] = {(cuuint64_t)v.rows, (cuuint64_t)v.in_ncols, (cuuint64_t)nmaps};
+  const cuuint64_t strides[2] = {(cuuint64_t)v.rows * sizeof(float), (cuuint64_t)v.rows * v.in_ncols * sizeof(float)};
+  const cuuint32_t box[3] = {(cuuint32_t)EROWS, (cuuint32_t)CH, 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  const CUresult cr = enc(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(elev), dims, strides, box, estr,
                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NAN_REQUEST_ZERO_FMA);
   if (cr != CUDA_SUCCESS) { st.why = "cuTensorMapEncodeTiled failed (" + std::to_string((int)cr) + ")"; return 1; }
@@ -911,12 +917,14 @@ int launch_chain_fused(FusedState& st, const SlabView& v, const ChainDev& p, con
   a.rows = v.rows; a.cols_total = v.cols_total;
   a.in_col0 = v.in_col0; a.in_ncols = v.in_ncols; a.out_col0 = v.out_col0; a.out_ncols = v.out_ncols;
   a.nstrips = (v.rows + OROWS - 1) / OROWS;
+  a.nmaps = nmaps;
+  a.map_cells = (unsigned)((size_t)v.rows * v.out_ncols);
   {
     const int total_warps = sms * WARPS_PER_CTA;
     const int nseg0 = std::max(1, (v.out_ncols + 199) / 200);
-    const long long units0 = (long long)a.nstrips * nseg0;
+    const long long units0 = (long long)a.nstrips * nseg0 * nmaps;
     const long long waves = (units0 + total_warps - 1) / total_warps;
-    long long nseg = std::max<long long>(1, waves * total_warps / a.nstrips);
+    long long nseg = std::max<long long>(1, waves * total_warps / ((long long)a.nstrips * nmaps));
     int seg_len = (int)((v.out_ncols + nseg - 1) / nseg);
     if (seg_len < 16) seg_len = std::min(16, v.out_ncols);
     a.seg_len = seg_len;
@@ -952,8 +960,9 @@ int launch_chain_fused(FusedState& st, const SlabView& v, const ChainDev& p, con
   a.k_m0 = B2(wn.w[2] >= 0 ? 2 * wn.w[2] + 1 : 0); a.k_m1 = B2(wn.w[1] >= 0 ? 2 * wn.w[1] + 1 : 0);
   a.k_one = B2(1.0); a.k_mone = B2(-1.0); a.k_two = B2(2.0); a.k_half = B2(0.5); a.k_mhalf = B2(-0.5); a.k_1p5 = B2(1.5);
   a.k_0375 = B2(0.375); a.k_m03125 = B2(-0.3125);
-  a.k_p0 = B2(0.16666752099990845); a.k_p1 = B2(0.07495298236608505); a.k_p2 = B2(0.045470330864191055);
-  a.k_p3 = B2(0.024179592728614807); a.k_p4 = B2(0.0421663373708725);
+  a.k_p0 = B2(1.570796251296997); a.k_p1 = B2(-0.21459604799747467); a.k_p2 = B2(0.08894557505846024);
+  a.k_p3 = B2(-0.05000271648168564); a.k_p4 = B2(0.03044925443828106); a.k_p5 = B2(-0.016484638676047325);
+  a.k_p6 = B2(0.006254698149859905); a.k_p7 = B2(-0.0011488182935863733);
   a.rowmask = (const unsigned char*)st.d_rowmask;
   a.colmask = (const unsigned char*)st.d_colmask;
   a.slope = o.slope; a.step = o.step; a.rough = o.rough; a.trav = o.trav;

@@ -28,6 +28,8 @@ bool fused_eligible(FusedState& st, const std::vector<double>& X, const std::vec
 // Arguments of the tier-2 fix-up kernel (te_fixup.cu): integer window description + parameters.
 struct FixupArgs {
   int rows, cols_total, in_col0, in_ncols, out_col0;
+  unsigned map_cells;       // output cells per map (batched launches index cells across maps)
+  size_t in_map_stride;     // elevation elements per map
   int wn[3], w1[3], w2[3];  // half-width per |column offset| (-1: column not in the window)
   int tip1, tip2;           // (+-2,0),(0,+-2) decided by the mask tables
   int ncrit;
@@ -44,7 +46,7 @@ void launch_fixup_t2(const FixupArgs& a, const float* elev, const ChainOut& o, c
                      unsigned cap, unsigned* list3, unsigned* count3, int sms, cudaStream_t s);
 
 // Returns 0 on success.  Cells whose result could not be certified in fp32 are appended to `list`.
-int launch_chain_fused(FusedState& st, const SlabView& v, const ChainDev& p, const float* elev, const ChainOut& o, unsigned* list,
-                       unsigned* count, unsigned cap, int sms, cudaStream_t s);
+int launch_chain_fused(FusedState& st, const SlabView& v, const ChainDev& p, int nmaps, const float* elev, const ChainOut& o,
+                       unsigned* list, unsigned* count, unsigned cap, int sms, cudaStream_t s);
 
 }  // namespace te

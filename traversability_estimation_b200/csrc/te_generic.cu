@@ -339,9 +339,15 @@ __global__ void __launch_bounds__(128) k_fixup_cells(SlabView v, ChainDev p, con
   for (unsigned int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
     const unsigned int w = list[k];
     const unsigned int c = w & 0x3fffffffu;  // bit 30: normals part, bit 31: step part
-    const int i = (int)(c % (unsigned)v.rows);
-    const int j = v.out_col0 + (int)(c / (unsigned)v.rows);
-    chain_cell_literal(v, p, elev, i, j, o, (w >> 30) & 1u, (w >> 31) & 1u);
+    const unsigned int map_cells = (unsigned)v.rows * (unsigned)v.out_ncols;
+    const unsigned int mapi = c / map_cells, cl = c - mapi * map_cells;  // batched launches index cells across maps
+    const int i = (int)(cl % (unsigned)v.rows);
+    const int j = v.out_col0 + (int)(cl / (unsigned)v.rows);
+    ChainOut om = o;
+    const size_t off = (size_t)mapi * map_cells;
+    om.slope += off; om.step += off; om.rough += off; om.trav += off;
+    if (om.nx) { om.nx += off; om.ny += off; om.nz += off; }
+    chain_cell_literal(v, p, elev + (size_t)mapi * v.rows * v.in_ncols, i, j, om, (w >> 30) & 1u, (w >> 31) & 1u);
   }
 }
 
