@@ -84,18 +84,26 @@ __device__ bool normals_t2(const FixupArgs& A, const Elev& E, int i, int j, floa
     fnx = fny = fnz = slope = rough = nanf_();
     return true;
   }
+  // gather the 5 x 5 neighbourhood once (25 independent loads), then work from registers
+  float zw[5][5];
+#pragma unroll
+  for (int l = -2; l <= 2; ++l)
+#pragma unroll
+    for (int k = -2; k <= 2; ++k) {
+      const int w = A.wn[l < 0 ? -l : l];
+      zw[l + 2][k + 2] = (k >= -w && k <= w) ? E(i + k, j + l) : nanf_();
+    }
   double n = 0, su = 0, sv = 0, sw = 0, suu = 0, suv = 0, svv = 0, suw = 0, svw = 0, sww = 0;
 #pragma unroll
-  for (int l = -2; l <= 2; ++l) {
-    const int w = A.wn[l < 0 ? -l : l];
-    for (int k = -w; k <= w; ++k) {
-      const float z = E(i + k, j + l);
+  for (int l = -2; l <= 2; ++l)
+#pragma unroll
+    for (int k = -2; k <= 2; ++k) {
+      const float z = zw[l + 2][k + 2];
       if (!finitef(z)) continue;
       const double u = -A.res * (double)k, v = -A.res * (double)l, d = (double)z - (double)zc;
       n += 1.0; su += u; sv += v; sw += d;
       suu += u * u; suv += u * v; svv += v * v; suw += u * d; svw += v * d; sww += d * d;
     }
-  }
   double nx = 0.0, ny = 0.0, nz = 1.0;
   const double mu = su / n, mv = sv / n, mw = sw / n;
   // scatter matrix sum (p - mean)(p - mean)^T
@@ -173,16 +181,15 @@ __device__ bool normals_t2(const FixupArgs& A, const Elev& E, int i, int j, floa
   double sum = 0.0, cnt = 0.0;
   const double plane = mu * NX + mv * NY + mw * NZ;
 #pragma unroll
-  for (int l = -2; l <= 2; ++l) {
-    const int w = A.wn[l < 0 ? -l : l];
-    for (int k = -w; k <= w; ++k) {
-      const float z = E(i + k, j + l);
+  for (int l = -2; l <= 2; ++l)
+#pragma unroll
+    for (int k = -2; k <= 2; ++k) {
+      const float z = zw[l + 2][k + 2];
       if (!finitef(z)) continue;
       const double d = NX * (-A.res * (double)k) + NY * (-A.res * (double)l) + NZ * ((double)z - (double)zc) - plane;
       sum += d * d;
       cnt += 1.0;
     }
-  }
   const double r = sqrt(sum / (cnt - 1.0));  // one point: 0/0 = NaN -> comparison false -> 0.0
   rough = (float)(r < A.rough_crit ? 1.0 - r / A.rough_crit : 0.0);
   return true;
