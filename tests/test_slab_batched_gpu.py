@@ -89,3 +89,22 @@ def test_size_independent_properties_at_scale(te, ctx):
     ctx.synchronize()
     assert torch.equal(torch.isnan(c[0]), hole)
     assert torch.equal(c[0][ok & torch.isfinite(c[0])], slope[ok & torch.isfinite(c[0])])  # slope/roughness windows have no on-circle offsets
+
+
+def test_pipelined_host_path_equals_device_path(te, ctx):
+    """te_chain(TE_MEM_HOST) on a large map runs as overlapped column chunks; it must equal the one-shot device result bitwise."""
+    import torch
+    import bench
+    rows, cols = 2048, 2304
+    z = bench.terrain_torch(torch, rows, 0, cols, cols, 9, 0.01, torch.device("cuda"))
+    g = te.Geometry.make(rows, cols, 0.02)
+    p = te.ChainParams.yaml_defaults(0)
+    ctx.set_stream(None)
+    dev = [torch.empty((cols, rows), dtype=torch.float32, device="cuda") for _ in range(4)]
+    ctx.chain(g, p, z, *dev, te.MEM_DEVICE)
+    ctx.synchronize()
+    h_in = z.cpu().pin_memory()
+    h_out = [torch.empty((cols, rows), dtype=torch.float32).pin_memory() for _ in range(4)]
+    ctx.chain(g, p, h_in.data_ptr(), *[o.data_ptr() for o in h_out], te.MEM_HOST)
+    for a, b in zip(dev, h_out):
+        assert torch.equal(a.cpu().view(torch.int32), b.view(torch.int32))

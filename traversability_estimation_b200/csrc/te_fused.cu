@@ -349,6 +349,8 @@ __device__ __forceinline__ Normal2 finish_normal2(const FusedArgs& A, f2 Sw, f2 
     const bool b_lam = (sww > 0.f) && !(R(lam0) > lthr);
     const bool b_cond = (sww > 0.f) && gap < A.cond_k * fmaxf(A.a_cov, R(c));
     bad |= b_lam || b_cond;
+    // a hole itself needs no second opinion: its slope/roughness are NaN by construction (see `inval` below)
+    bad = bad && (fabsf(R(ec)) < 3.0e38f);
     flag |= bad ? (1u << k) : 0u;
     if (A.stats) flag |= ((b_inv ? 1u : 0u) | (b_lam ? 2u : 0u) | (b_cond ? 4u : 0u)) << (2 + 4 * k);
   }
@@ -368,13 +370,13 @@ __device__ __forceinline__ Normal2 finish_normal2(const FusedArgs& A, f2 Sw, f2 
     }
   }
   const f2 theta = acos2(A, nz);
-  o.nz = nz;
   // layer = x < crit ? 1 - x/crit : 0  ==  max(1 - x/crit, 0)
   const f2 sl = fma2(theta, A.k_minv_slope, A.k_one);
   const f2 ro = fma2(r, A.k_minv_rough, A.k_one);
   // a hole (invalid centre: NaN, or Inf - Inf) has no normal: slope and roughness stay NaN
-  // (SlopeFilter.cpp:71, RoughnessFilter.cpp:84); such cells are flagged by the Sww test and tier 2 confirms the NaN
+  // (SlopeFilter.cpp:71, RoughnessFilter.cpp:84) and the cell is not flagged
   const f2 inval = sub2(ec, ec);
+  o.nz = add2(nz, inval);
   o.slope = add2(mk(fmaxf(lo(sl), 0.0f), fmaxf(hi(sl), 0.0f)), inval);
   o.rough = add2(mk(fmaxf(lo(ro), 0.0f), fmaxf(hi(ro), 0.0f)), inval);
   o.flag = flag;
