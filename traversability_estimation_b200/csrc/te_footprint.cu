@@ -14,7 +14,9 @@
 // Layers are column-major float32; the slab/halo conventions are those of te_chain.
 #include "te_footprint.h"
 
+#include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 namespace te {
@@ -37,6 +39,17 @@ struct FpArgs {
   int n_spiral;
   const int* spiral;  // di & 0xff | (dj & 0xff) << 8 | edge << 16
   int slope_R, step_R;
+  // prefix-sum sweep (k_fp_prepare / k_sweep_fast)
+  int L;                      // max |column offset| of the certain-in disk
+  int nrings;                 // SpiralIterator nRings
+  const signed char* halfw;   // [2L+1]: half-width of the certain-in disk per column offset (-1: none)
+  const signed char* inner;   // [(nrings+2) x (2L+1)]: half-width of {k^2+l^2 < d^2} intersected with the disk, per ring d
+  const int* ring_start;      // [nrings+2]: first index of ring d in `spiral`
+  int n_fuzzy;                // offsets lying exactly on the circle: decided per cell on absolute positions
+  const int* fuzzy;           // same packing as `spiral`
+  const double* P;            // per input-buffer column: rows+1 prefix sums of t' along the row index
+  const unsigned* bits;       // per input-buffer column: (rows+31)/32 words of blocked flags
+  int words;                  // words per column
 };
 
 __device__ __forceinline__ float lay(const FpArgs& A, const float* l, int i, int j) {  // caller guarantees (i,j) is in the map
@@ -266,6 +279,153 @@ __global__ void __launch_bounds__(256) k_sweep(FpArgs A, Layers L, const unsigne
   }
 }
 
+// One warp per input-buffer column: prefix sums of t' = finite(traversability) ? value : default along the row
+// index (double; exact for float32 terms, so the order of summation does not matter) and packed blocked flags.
+__global__ void __launch_bounds__(256) k_fp_prepare(FpArgs A, Layers L, const unsigned char* __restrict__ blocked, double* __restrict__ P,
+                                                    unsigned* __restrict__ bits) {
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int lb = warp; lb < A.in_ncols; lb += nwarps) {
+    const float* tcol = L.trav + (size_t)lb * A.rows;
+    const unsigned char* bcol = blocked + (size_t)lb * A.rows;
+    double* pcol = P + (size_t)lb * (A.rows + 1);
+    unsigned* wcol = bits + (size_t)lb * A.words;
+    double carry = 0.0;
+    if (lane == 0) pcol[0] = 0.0;
+    for (int base = 0; base < A.rows; base += 32) {
+      const int i = base + lane;
+      double v = 0.0;
+      bool b = false;
+      if (i < A.rows) {
+        const float t = __ldg(tcol + i);
+        v = finitef(t) ? (double)t : A.tdefault;
+        b = bcol[i] != 0;
+      }
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const double o = __shfl_up_sync(0xffffffffu, v, d);
+        if (lane >= d) v += o;
+      }
+      if (i < A.rows) pcol[i + 1] = carry + v;
+      const unsigned w = __ballot_sync(0xffffffffu, b);
+      if (lane == 0) wcol[base >> 5] = w;
+      carry += __shfl_sync(0xffffffffu, v, 31);
+    }
+  }
+}
+
+// isTraversable for every cell on prefix sums: the visited set is a lattice disk, so "is anything blocked in it"
+// and "sum / count of the visited cells" are 2L+1 column queries instead of ~pi r^2 visits; only when a blocker
+// exists is the ring that holds the first one walked in SpiralIterator order.
+__global__ void __launch_bounds__(256) k_sweep_fast(FpArgs A, Layers L, const unsigned char* __restrict__ blocked, float* __restrict__ out) {
+  const long long total = (long long)A.rows * A.out_ncols;
+  const int W = 2 * A.L + 1;
+  for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < total; c += (long long)gridDim.x * blockDim.x) {
+    const int i = (int)(c % A.rows);
+    const int j = A.out_col0 + (int)(c / A.rows);
+    const double cx = A.X[i], cy = A.Y[j];
+    // ---- nearest blocked cell of the visited set, as a squared index distance ------------------------
+    int best = 0x7fffffff;
+    const int r0 = i - 31;                      // window of 64 rows [r0, r0+64) around the centre (needs L <= 31)
+    const int w0 = r0 >> 5, sh = r0 & 31;       // arithmetic shift: rows < 0 live in words < 0
+    for (int l = -A.L; l <= A.L; ++l) {
+      const int b = j + l, lb = b - A.in_col0;
+      const int hw = A.halfw[l + A.L];
+      if (hw < 0 || b < 0 || b >= A.cols_total || lb < 0 || lb >= A.in_ncols) continue;
+      const unsigned* wcol = A.bits + (size_t)lb * A.words;
+      unsigned long long lo = 0ull, hi = 0ull;
+      {
+        const unsigned a0 = (w0 >= 0 && w0 < A.words) ? __ldg(wcol + w0) : 0u;
+        const unsigned a1 = (w0 + 1 >= 0 && w0 + 1 < A.words) ? __ldg(wcol + w0 + 1) : 0u;
+        const unsigned a2 = (w0 + 2 >= 0 && w0 + 2 < A.words) ? __ldg(wcol + w0 + 2) : 0u;
+        lo = ((unsigned long long)a1 << 32) | a0;
+        hi = a2;
+      }
+      unsigned long long f = (lo >> sh) | (sh ? (hi << (64 - sh)) : 0ull);  // bit t <-> row r0 + t ; centre at bit 31
+      // keep rows i-hw .. i+hw
+      const unsigned long long m = ((1ull << (2 * hw + 1)) - 1ull) << (31 - hw);  // hw <= 31
+      f &= m;
+      if (!f) continue;
+      const unsigned long long up = f >> 31;                  // k >= 0 at bit k
+      const unsigned long long dn = f & ((1ull << 31) - 1ull); // k < 0: row i+k at bit 31+k
+      int kmin = 64;
+      if (up) kmin = __ffsll((long long)up) - 1;
+      if (dn) kmin = min(kmin, 31 - (63 - __clzll((long long)dn)));
+      best = min(best, kmin * kmin + l * l);
+    }
+    for (int q = 0; q < A.n_fuzzy; ++q) {
+      const int w = A.fuzzy[q];
+      const int di = (int)(signed char)(w & 0xff), dj = (int)(signed char)((w >> 8) & 0xff);
+      const int a = i + di, b = j + dj, lb = b - A.in_col0;
+      if (a < 0 || b < 0 || a >= A.rows || b >= A.cols_total || lb < 0 || lb >= A.in_ncols) continue;
+      const double dx = A.X[a] - cx, dy = A.Y[b] - cy;
+      if (!(dx * dx + dy * dy <= A.rmax2)) continue;
+      if (blocked[(size_t)lb * A.rows + a]) best = min(best, di * di + dj * dj);
+    }
+    // ---- sums over the visited cells before the first blocked one --------------------------------------
+    const bool any = best != 0x7fffffff;
+    const int dstar = any ? (int)sqrt((double)best) : A.nrings + 1;  // ring of the first blocked cell
+    const signed char* hwt = any ? (A.inner + (size_t)dstar * W) : A.halfw;
+    double t = 0.0;
+    int n = 0;
+    for (int l = -A.L; l <= A.L; ++l) {
+      const int b = j + l, lb = b - A.in_col0;
+      const int hw = hwt[l + A.L];
+      if (hw < 0 || b < 0 || b >= A.cols_total || lb < 0 || lb >= A.in_ncols) continue;
+      const int a0 = max(i - hw, 0), a1 = min(i + hw, A.rows - 1);
+      const double* pcol = A.P + (size_t)lb * (A.rows + 1);
+      t += pcol[a1 + 1] - pcol[a0];
+      n += a1 - a0 + 1;
+    }
+    float result;
+    if (!any) {
+      for (int q = 0; q < A.n_fuzzy; ++q) {  // on-circle cells belong to the last ring: they are visited last
+        const int w = A.fuzzy[q];
+        const int di = (int)(signed char)(w & 0xff), dj = (int)(signed char)((w >> 8) & 0xff);
+        const int a = i + di, b = j + dj, lb = b - A.in_col0;
+        if (a < 0 || b < 0 || a >= A.rows || b >= A.cols_total || lb < 0 || lb >= A.in_ncols) continue;
+        const double dx = A.X[a] - cx, dy = A.Y[b] - cy;
+        if (!(dx * dx + dy * dy <= A.rmax2)) continue;
+        const float v = __ldg(L.trav + (size_t)lb * A.rows + a);
+        t += finitef(v) ? (double)v : A.tdefault;
+        ++n;
+      }
+      t /= (double)n;
+      result = (float)t;
+    } else {
+      // walk ring dstar in visit order up to its first blocked cell
+      int di = 0, dj = 0;
+      for (int k = A.ring_start[dstar]; k < A.ring_start[dstar + 1]; ++k) {
+        const int w = __ldg(A.spiral + k);
+        di = (int)(signed char)(w & 0xff);
+        dj = (int)(signed char)((w >> 8) & 0xff);
+        const int a = i + di, b = j + dj, lb = b - A.in_col0;
+        if (a < 0 || b < 0 || a >= A.rows || b >= A.cols_total || lb < 0 || lb >= A.in_ncols) continue;
+        if (w & 0x10000) {
+          const double dx = A.X[a] - cx, dy = A.Y[b] - cy;
+          if (!(dx * dx + dy * dy <= A.rmax2)) continue;
+        }
+        const size_t cc = (size_t)lb * A.rows + a;
+        if (blocked[cc]) break;
+        const float v = __ldg(L.trav + cc);
+        t += finitef(v) ? (double)v : A.tdefault;
+        ++n;
+      }
+      const int d2 = di * di + dj * dj;
+      const double nr = A.int_norm ? (double)(int)sqrt((double)d2) : sqrt((double)d2);
+      const double uR = nr * A.res;
+      if (A.rmin == 0.0 || uR <= A.rmin) {
+        result = 0.0f;
+      } else {
+        const double factor = ((uR - A.rmin) / (A.rmax - A.rmin) + 1.0) / 2.0;
+        t *= factor / (double)n;
+        result = (float)t;
+      }
+    }
+    out[c] = result;
+  }
+}
+
 inline int signum(int v) { return (0 < v) - (v < 0); }
 
 // grid_map::SpiralIterator::generateRing, executed literally.
@@ -294,8 +454,11 @@ std::vector<int> build_spiral(double radius, double res) {
 void FootprintState::release() {
   if (d_spiral) cudaFree(d_spiral);
   if (d_block) cudaFree(d_block);
-  d_spiral = d_block = nullptr;
-  spiral_cap = block_cap = 0;
+  if (d_tables) cudaFree(d_tables);
+  if (d_prefix) cudaFree(d_prefix);
+  d_spiral = d_block = d_tables = d_prefix = nullptr;
+  spiral_cap = block_cap = tables_cap = prefix_cap = 0;
+  tables_valid = false;
   valid = false;
 }
 
@@ -329,6 +492,7 @@ int launch_footprint(FootprintState& st, const SlabView& v, const te_geometry* g
     st.key_geo = *g;
     st.key_par = *p;
     st.valid = true;
+    st.tables_valid = false;
   }
   const size_t ncell_in = (size_t)v.rows * v.in_ncols;
   if (st.block_cap < ncell_in) {
@@ -353,8 +517,90 @@ int launch_footprint(FootprintState& st, const SlabView& v, const te_geometry* g
   const int g1 = (int)std::min<long long>((t1 + 127) / 128, (long long)sms * 16);
   const int g2 = (int)std::min<long long>((t2 + 255) / 256, (long long)sms * 8);
   k_predicates<<<std::max(g1, 1), 128, 0, s>>>(a, L, (unsigned char*)st.d_block, slope_fp, step_fp);
-  k_sweep<<<std::max(g2, 1), 256, 0, s>>>(a, L, (const unsigned char*)st.d_block, out);
-  if (launches) *launches = 2;
+  const int Lmax = (int)std::floor(rmax / g->resolution + 1e-9);
+  const bool fast = Lmax <= 31 && std::getenv("TE_FOOTPRINT_BRUTE") == nullptr;
+  if (!fast) {
+    k_sweep<<<std::max(g2, 1), 256, 0, s>>>(a, L, (const unsigned char*)st.d_block, out);
+    if (launches) *launches = 2;
+    return 0;
+  }
+  // ---- prefix-sum sweep: tables (cached with the spiral) + per-call prefix/bit arrays -----------------
+  if (!st.tables_valid) {
+    const double res = g->resolution, r2 = rmax * rmax, tol = 1e-9 * r2 + 1e-300;
+    const int nR = (int)std::ceil(rmax / res), Wd = 2 * Lmax + 1;
+    std::vector<signed char> halfw(Wd, -1), inner((size_t)(nR + 2) * Wd, -1);
+    std::vector<int> fuzzy, ring_start(nR + 2, 0);
+    for (int l = -Lmax; l <= Lmax; ++l)
+      for (int k = -Lmax - 1; k <= Lmax + 1; ++k) {
+        const double d2 = (double)(k * k + l * l) * res * res;
+        if (d2 < r2 - tol) halfw[l + Lmax] = (signed char)std::max<int>(halfw[l + Lmax], std::abs(k));
+        else if (std::fabs(d2 - r2) <= tol && k >= -Lmax && k <= Lmax) fuzzy.push_back((k & 0xff) | ((l & 0xff) << 8) | 0x10000);
+      }
+    for (int d = 0; d <= nR + 1; ++d)
+      for (int l = -Lmax; l <= Lmax; ++l) {
+        int u = -1;
+        for (int k = 0; k <= halfw[l + Lmax]; ++k)
+          if (k * k + l * l < d * d) u = k;
+        inner[(size_t)d * Wd + l + Lmax] = (signed char)u;
+      }
+    {  // ring boundaries of the spiral table: ring d = entries with floor(|offset|) == d, in table order
+      const std::vector<int> sp = build_spiral(rmax, res);
+      int idx = 0;
+      for (int d = 0; d <= nR; ++d) {
+        ring_start[d] = idx;
+        while (idx < (int)sp.size()) {
+          const int di = (int)(signed char)(sp[idx] & 0xff), dj = (int)(signed char)((sp[idx] >> 8) & 0xff);
+          if ((int)std::sqrt((double)(di * di + dj * dj)) != d) break;
+          ++idx;
+        }
+      }
+      ring_start[nR + 1] = idx;
+    }
+    const size_t bytes = halfw.size() + inner.size() + 4 * (fuzzy.size() + 1) + 4 * ring_start.size() + 64;
+    if (st.tables_cap < bytes) {
+      if (st.d_tables) cudaFree(st.d_tables);
+      st.d_tables = nullptr; st.tables_cap = 0;
+      if (cudaMalloc(&st.d_tables, bytes) != cudaSuccess) { st.why = "cudaMalloc(footprint tables) failed"; return TE_ERR_CUDA; }
+      st.tables_cap = bytes;
+    }
+    char* base = (char*)st.d_tables;
+    size_t off = 0;
+    auto put = [&](const void* src, size_t n, size_t align) {
+      off = (off + align - 1) / align * align;
+      cudaMemcpyAsync(base + off, src, n, cudaMemcpyHostToDevice, s);
+      const size_t at = off;
+      off += n;
+      return at;
+    };
+    st.off_ring = put(ring_start.data(), 4 * ring_start.size(), 4);
+    st.off_fuzzy = put(fuzzy.empty() ? (const void*)ring_start.data() : (const void*)fuzzy.data(), 4 * std::max<size_t>(fuzzy.size(), 1), 4);
+    st.off_halfw = put(halfw.data(), halfw.size(), 1);
+    st.off_inner = put(inner.data(), inner.size(), 1);
+    if (cudaStreamSynchronize(s) != cudaSuccess) { st.why = "footprint table upload failed"; return TE_ERR_CUDA; }
+    st.n_fuzzy = (int)fuzzy.size();
+    st.L = Lmax;
+    st.nrings = nR;
+    st.tables_valid = true;
+  }
+  const int words = (v.rows + 31) / 32;
+  const size_t pbytes = sizeof(double) * (size_t)(v.rows + 1) * v.in_ncols, wbytes = sizeof(unsigned) * (size_t)words * v.in_ncols;
+  if (st.prefix_cap < pbytes + wbytes) {
+    if (st.d_prefix) cudaFree(st.d_prefix);
+    st.d_prefix = nullptr; st.prefix_cap = 0;
+    if (cudaMalloc(&st.d_prefix, pbytes + wbytes) != cudaSuccess) { st.why = "cudaMalloc(footprint prefix sums) failed"; return TE_ERR_CUDA; }
+    st.prefix_cap = pbytes + wbytes;
+  }
+  a.L = st.L; a.nrings = st.nrings; a.n_fuzzy = st.n_fuzzy; a.words = words;
+  a.ring_start = (const int*)((char*)st.d_tables + st.off_ring);
+  a.fuzzy = (const int*)((char*)st.d_tables + st.off_fuzzy);
+  a.halfw = (const signed char*)((char*)st.d_tables + st.off_halfw);
+  a.inner = (const signed char*)((char*)st.d_tables + st.off_inner);
+  a.P = (const double*)st.d_prefix;
+  a.bits = (const unsigned*)((char*)st.d_prefix + pbytes);
+  const int g3 = std::min(sms * 8, (v.in_ncols + 7) / 8);
+  k_fp_prepare<<<std::max(g3, 1), 256, 0, s>>>(a, L, (const unsigned char*)st.d_block, (double*)st.d_prefix, (unsigned*)((char*)st.d_prefix + pbytes));
+  k_sweep_fast<<<std::max(g2, 1), 256, 0, s>>>(a, L, (const unsigned char*)st.d_block, out);
+  if (launches) *launches = 3;
   return 0;
 }
 

@@ -18,7 +18,15 @@ struct FootprintState {
   int n_spiral = 0;
   void* d_block = nullptr;   // per-cell predicate bytes for the slab + halo
   size_t block_cap = 0;
-  void invalidate() { valid = false; }
+  // prefix-sum sweep: half-width / ring tables (depend on radius and resolution) and per-call prefix sums + bit columns
+  void* d_tables = nullptr;
+  size_t tables_cap = 0;
+  bool tables_valid = false;
+  size_t off_ring = 0, off_fuzzy = 0, off_halfw = 0, off_inner = 0;
+  int n_fuzzy = 0, L = 0, nrings = 0;
+  void* d_prefix = nullptr;
+  size_t prefix_cap = 0;
+  void invalidate() { valid = false; tables_valid = false; }
   void release();
 };
 

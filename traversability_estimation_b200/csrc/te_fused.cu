@@ -47,6 +47,11 @@ constexpr int WARP_SMEM_BYTES = NST * STAGE_BYTES + 2 * SHBUF_BYTES + 64;  // 62
 #define TE_WPC 12
 #endif
 constexpr int WARPS_PER_CTA = TE_WPC;
+#ifdef TE_REGS
+#define TE_KERNEL_ATTR __maxnreg__(TE_REGS)
+#else
+#define TE_KERNEL_ATTR __launch_bounds__(WARPS_PER_CTA * 32, 1)
+#endif
 constexpr unsigned FULL = 0xffffffffu;
 
 typedef unsigned long long f2;  // two packed floats in one aligned register pair (see below)
@@ -637,7 +642,7 @@ __device__ __forceinline__ void march_step(StepCtx<S>& C, Lane<S>& L, int t, uns
 }
 
 template <class S>
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 1) k_chain_fused(const __grid_constant__ CUtensorMap map, FusedArgs A) {
+__global__ void TE_KERNEL_ATTR k_chain_fused(const __grid_constant__ CUtensorMap map, FusedArgs A) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int warp = __shfl_sync(FULL, (int)(threadIdx.x >> 5), 0);  // provably warp-uniform: uniform datapath for the control flow
   const int lane = threadIdx.x & 31;
