@@ -242,7 +242,7 @@ __global__ void __launch_bounds__(128) k_fixup_t2(FixupArgs A, const float* __re
 
 void launch_fixup_t2(const FixupArgs& a, const float* elev, const ChainOut& o, const unsigned* list, const unsigned* count,
                      unsigned cap, unsigned* list3, unsigned* count3, int sms, cudaStream_t s) {
-  k_fixup_t2<<<sms * 8, 128, 0, s>>>(a, elev, o, list, count, cap, list3, count3);
+  k_fixup_t2<<<sms * 64, 128, 0, s>>>(a, elev, o, list, count, cap, list3, count3);  // ~1.2 M threads: one listed cell each, latency hidden by occupancy
 }
 
 }  // namespace te
