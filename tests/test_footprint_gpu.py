@@ -74,3 +74,33 @@ def test_footprint_matches_oracle_on_chain_outputs(te, ctx, oracle, case):
         assert _same(a, b), (name, int((np.isnan(a) != np.isnan(b)).sum()), float(np.nanmax(np.abs(a - b))))
     assert (ref[0] == 0).any() and (ref[0] > 0).any()
     assert np.isfinite(ref[2]).sum() > 0  # step == 0 cells exist, so the gap walk was exercised
+
+
+def test_footprint_slabs_equal_whole_map(te, ctx, oracle):
+    """Multi-GPU tiling of the sweep: a column slab with a 43-column halo gives exactly the whole-map result."""
+    import torch
+    rows, cols = 128, 300
+    z = synth.terrain(rows, cols, 0.02, 41, "mixed")
+    og = oracle.Geometry.make(rows, cols, 0.02)
+    g = te.Geometry.make(rows, cols, 0.02)
+    ch = oracle.chain(og, oracle.ChainParams.yaml_defaults(0), z)
+    fp = te.FootprintParams.yaml_defaults()
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(np.asarray(a, dtype=np.float32).T)).cuda()  # noqa: E731
+    lay = [dev(ch["traversability"]), dev(ch["slope"]), dev(ch["step"]), dev(z)]
+    ctx.set_stream(None)
+    whole = torch.empty((cols, rows), dtype=torch.float32, device="cuda")
+    ctx.footprint(g, fp, *lay, whole, te.MEM_DEVICE)
+    ctx.synchronize()
+    H = 43
+    for b, e in ((0, 140), (140, 300)):
+        hl, hr = min(H, b), min(H, cols - e)
+        part = [x[b - hl:e + hr].contiguous() for x in lay]
+        out = torch.empty((e - b, rows), dtype=torch.float32, device="cuda")
+        ctx.footprint(g, fp, *part, out, te.MEM_DEVICE, slab=te.Slab(b, e - b, hl, hr))
+        ctx.synchronize()
+        a, c = whole[b:e], out
+        assert torch.equal(torch.isnan(a), torch.isnan(c))
+        assert torch.equal(a[~torch.isnan(a)], c[~torch.isnan(c)]), (b, e)
+    with pytest.raises(te.TEError):
+        ctx.footprint(g, fp, *[x[130:300].contiguous() for x in lay], torch.empty((160, rows), dtype=torch.float32, device="cuda"),
+                      te.MEM_DEVICE, slab=te.Slab(140, 160, 10, 0))
