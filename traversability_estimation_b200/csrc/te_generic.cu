@@ -157,7 +157,8 @@ __device__ void jacobi3(const double ain[3][3], double eval[3], double evec[3][3
 }
 
 // NormalVectorsFilter area method at one cell whose elevation is finite.
-__device__ void normal_literal(const SlabView& v, const ChainDev& p, const ElevAccess& E, int i, int j, double n[3]) {
+template <class Acc>
+__device__ void normal_literal(const SlabView& v, const ChainDev& p, const Acc& E, int i, int j, double n[3]) {
   n[0] = 0.0; n[1] = 0.0; n[2] = 1.0;
   if (p.alg == 0) {
     double sx = 0.0, sy = 0.0, sz = 0.0;
@@ -258,7 +259,8 @@ __device__ float step_literal(const SlabView& v, const ChainDev& p, const ElevAc
   return (float)(step < p.step_crit ? 1.0 - step / p.step_crit : 0.0);
 }
 
-__device__ float roughness_literal(const SlabView& v, const ChainDev& p, const ElevAccess& E, int i, int j,
+template <class Acc>
+__device__ float roughness_literal(const SlabView& v, const ChainDev& p, const Acc& E, int i, int j,
                                    float fnx, float fny, float fnz) {
   if (!finitef(fnx)) return nanf_();
   double sx = 0.0, sy = 0.0, sz = 0.0;
@@ -283,6 +285,25 @@ __device__ float roughness_literal(const SlabView& v, const ChainDev& p, const E
   return (float)(rough < p.rough_crit ? 1.0 - rough / p.rough_crit : 0.0);
 }
 
+// The 7 x 7 neighbourhood of one cell fetched up front (49 independent loads) so that the literal arithmetic of a
+// lone fix-up cell is not a chain of dependent memory latencies.
+struct ElevWindow {
+  float z[7][7];
+  int i0, j0;
+  __device__ __forceinline__ void fill(const ElevAccess& E, int i, int j) {
+    i0 = i - 3;
+    j0 = j - 3;
+#pragma unroll
+    for (int b = 0; b < 7; ++b)
+#pragma unroll
+      for (int a = 0; a < 7; ++a) z[b][a] = E(i0 + a, j0 + b);
+  }
+  __device__ __forceinline__ float operator()(int a, int b) const {  // dynamic index: the array lives in (L1-cached) local memory
+    const unsigned da = (unsigned)(a - i0), db = (unsigned)(b - j0);
+    return (da < 7u && db < 7u) ? z[db][da] : nanf_();
+  }
+};
+
 __device__ __forceinline__ ElevAccess make_access(const SlabView& v, const float* e) {
   return ElevAccess{e, v.rows, v.in_col0, v.in_ncols, v.cols_total};
 }
@@ -290,19 +311,31 @@ __device__ __forceinline__ ElevAccess make_access(const SlabView& v, const float
 // One cell of the whole chain.  The fix-up pass of the fused stencil recomputes only the part it
 // could not certify (normals/slope/roughness and/or step) and always re-fuses.
 __device__ void chain_cell_literal(const SlabView& v, const ChainDev& p, const float* elev, int i, int j,
-                                   ChainOut o, bool do_normals, bool do_step) {
+                                   ChainOut o, bool do_normals, bool do_step, bool use_window = false) {
   const ElevAccess E = make_access(v, elev);
   const size_t oc = (size_t)(j - v.out_col0) * v.rows + i;
   float s, r, t;
   if (do_normals) {
     float fnx = nanf_(), fny = nanf_(), fnz = nanf_();
-    if (finitef(E(i, j))) {
-      double n[3];
-      normal_literal(v, p, E, i, j, n);
-      fnx = (float)n[0]; fny = (float)n[1]; fnz = (float)n[2];
+    if (use_window && p.Rn <= 3 && p.Rr <= 3) {
+      ElevWindow Wn;
+      Wn.fill(E, i, j);
+      if (finitef(Wn(i, j))) {
+        double n[3];
+        normal_literal(v, p, Wn, i, j, n);
+        fnx = (float)n[0]; fny = (float)n[1]; fnz = (float)n[2];
+      }
+      s = slope_literal(fnz, p.slope_crit);
+      r = roughness_literal(v, p, Wn, i, j, fnx, fny, fnz);
+    } else {
+      if (finitef(E(i, j))) {
+        double n[3];
+        normal_literal(v, p, E, i, j, n);
+        fnx = (float)n[0]; fny = (float)n[1]; fnz = (float)n[2];
+      }
+      s = slope_literal(fnz, p.slope_crit);
+      r = roughness_literal(v, p, E, i, j, fnx, fny, fnz);
     }
-    s = slope_literal(fnz, p.slope_crit);
-    r = roughness_literal(v, p, E, i, j, fnx, fny, fnz);
     o.slope[oc] = s;
     o.rough[oc] = r;
     if (o.nx) o.nx[oc] = fnx;
@@ -347,7 +380,7 @@ __global__ void __launch_bounds__(128) k_fixup_cells(SlabView v, ChainDev p, con
     const size_t off = (size_t)mapi * map_cells;
     om.slope += off; om.step += off; om.rough += off; om.trav += off;
     if (om.nx) { om.nx += off; om.ny += off; om.nz += off; }
-    chain_cell_literal(v, p, elev + (size_t)mapi * v.rows * v.in_ncols, i, j, om, (w >> 30) & 1u, (w >> 31) & 1u);
+    chain_cell_literal(v, p, elev + (size_t)mapi * v.rows * v.in_ncols, i, j, om, (w >> 30) & 1u, (w >> 31) & 1u, true);
   }
 }
 
