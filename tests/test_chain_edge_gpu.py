@@ -104,3 +104,33 @@ def test_standalone_filters_match_oracle(te, ctx, oracle):
     with pytest.raises(te.TEError) as e:   # missing layer -> TE_ERR_MISSING_LAYER
         ctx.roughness(g, pt, z, None, ny, nz, r, te.MEM_HOST)
     assert e.value.code == -2
+
+
+def test_fused_against_literal_kernel_at_scale(te, ctx):
+    """16.7 M cells: the fused stencil (fp32 + certification ladder) against the literal double-precision kernel, which is
+    bit-exact against the oracle at every size the oracle can check.  No cell may leave the tolerance."""
+    import torch
+    import bench
+    rows = cols = 4096
+    z = bench.terrain_torch(torch, rows, 0, cols, cols, 11, 0.01, torch.device("cuda"))
+    g = te.Geometry.make(rows, cols, 0.02)
+    p = te.ChainParams.yaml_defaults(0)
+    ctx.set_stream(None)
+    res = {}
+    for name, kernel in (("fused", te.KERNEL_FUSED), ("literal", te.KERNEL_GENERIC)):
+        ctx.set_kernel(kernel)
+        outs = [torch.empty((cols, rows), dtype=torch.float32, device="cuda") for _ in range(4)]
+        ctx.chain(g, p, z, *outs, te.MEM_DEVICE)
+        ctx.synchronize()
+        res[name] = outs
+    ctx.set_kernel(te.KERNEL_AUTO)
+    worst = {}
+    for k, a, b in zip(("slope", "step", "roughness", "traversability"), res["fused"], res["literal"]):
+        assert torch.equal(torch.isnan(a), torch.isnan(b)), k
+        ok = ~torch.isnan(b)
+        d = (a[ok].double() - b[ok].double()).abs()
+        tol = 1e-5 * b[ok].double().abs() + 1e-6
+        bad = int((d > tol).sum())
+        worst[k] = (bad, float((d / tol).max()))
+        assert bad == 0, (k, bad, float(d.max()))
+    print(worst)
