@@ -73,9 +73,9 @@ struct FusedArgs {
   float rough_crit, inv_rough_crit;
   float fuse_w;
   float cond_k;     // eigen-gap / scale ratio below which the fp32 eigenvector is not trusted
-  int stats;        // 1: count[1..3] += cells flagged per cause (lambda0, conditioning, small-angle rounding)
   // constants pre-broadcast to both halves of a register pair (one LDC.64 each)
   f2 k_invN, k_minvN, k_kp, k_half_a, k_nnm1, k_rough_thr, k_minv_slope, k_minv_rough, k_m0, k_m1;
+  f2 k_1em5, k_1em10a, k_mcond;
   f2 k_one, k_mone, k_two, k_half, k_mhalf, k_1p5, k_0375, k_m03125, k_p0, k_p1, k_p2, k_p3, k_p4, k_p5, k_p6, k_p7;
   const unsigned char* rowmask;  // per global row: bit0/1 pass-1 tips (-2,0)/(+2,0); bit2/3 pass-2 tips
   const unsigned char* colmask;  // per global column, same bits for (0,-2)/(0,+2)
@@ -296,6 +296,22 @@ __device__ __forceinline__ f2 acos2(const FusedArgs& A, f2 x) {
   return mul2(sq, p);
 }
 
+// NaN-propagating min (a NaN margin must fail the certification)
+__device__ __forceinline__ float min2n(float a, float b) {
+  float r;
+  asm("min.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+  return r;
+}
+// n_z = 1 - s is rounded to float32 with spacing 2^-24: true when s, known to relative error eps, may sit on the other
+// side of a rounding boundary.  eps: the first moments carry <= 2.5e-6*sqrt(Sww) absolute error.  Rare: kept out of line.
+__device__ __noinline__ bool cert_rounding(float s, float sk, float sl, float sww) {
+  const float qv = s * 16777216.0f;
+  const float fr = qv - floorf(qv);
+  const float gm2 = fmaf(sk, sk, sl * sl);
+  const float eps = fmaf(7.1e-6f, sqrt_a(sww * rcp_a(fmaxf(gm2, 1e-36f))), 2e-6f);
+  return fabsf(fr - 0.5f) <= fmaf(qv, eps, 1e-3f);
+}
+
 // Closed-form smallest eigenpair of the scatter matrix [[a,0,p],[0,a,q],[p,q,c]] of a full disk
 // window for both rows of the lane, slope and roughness layers, and the certification of all of it.
 __device__ __forceinline__ Normal2 finish_normal2(const FusedArgs& A, f2 Sw, f2 Sk, f2 Sl, f2 Sww, f2 ec) {
@@ -338,49 +354,31 @@ __device__ __forceinline__ Normal2 finish_normal2(const FusedArgs& A, f2 Sw, f2 
   const f2 nzs = sub2(A.k_one, s);
   const bool smx = hx && lo(t) < 2.5e-3f, smy = hy && hi(t) < 2.5e-3f;
   const f2 nz = mk(fminf(smx ? lo(nzs) : lo(nzg), 1.0f), fminf(smy ? hi(nzs) : hi(nzg), 1.0f));
+  // ---- certification (packed margins; a NaN margin fails) ----------------------------------------------------------
+  // rank / roughness: lambda0 must stand clear of its cancellation error (1e-5 cmag), of the reference's rank-threshold
+  // region (1e-10 a) and of what the roughness tolerance allows (thr); conditioning: the eigen-gap min(2D, m) against
+  // the matrix scale.  Invalid windows (NaN/Inf moments) fail through NaN; exactly flat windows (Sww == 0) are exact;
+  // holes (invalid centre) need no second opinion.
+  const f2 lbase = fma2(cmag, A.k_1em5, A.k_1em10a);
+  const f2 t1 = sub2(lam0, mk(fmaxf(lo(lbase), lo(thr)), fmaxf(hi(lbase), hi(thr))));
+  const f2 D2 = add2(D, D);
+  const f2 t2 = fma2(mk(fmaxf(A.a_cov, lo(c)), fmaxf(A.a_cov, hi(c))), A.k_mcond, mk(fminf(lo(D2), lo(m)), fminf(hi(D2), hi(m))));
+  const f2 inval = sub2(ec, ec);
   unsigned flag = 0;
-#pragma unroll
-  for (int k = 0; k < 2; ++k) {
-    auto R = [&](f2 v) { return k ? hi(v) : lo(v); };
-    const float sww = R(Sww), cm = R(cmag);
-    // invalid window (NaN/Inf poisoning, overflow) or degenerate pencil
-    const bool b_inv = !(sww < 3.0e38f) || !(R(nn) > 0.f);
-    bool bad = b_inv;
-    // rank / roughness: lambda0 must stand clear of the cancellation error (1e-5 cmag), of the
-    // reference's rank-threshold region (1e-10 a) and of what the roughness tolerance allows;
-    // conditioning: eigen-gap min(2D, m) against the matrix scale.  Exactly flat windows are exact.
-    const float lthr = fmaxf(fmaxf(1e-5f * cm, 1e-10f * A.a_cov), R(thr));
-    const float gap = fminf(2.0f * R(D), R(m));
-    const bool b_lam = (sww > 0.f) && !(R(lam0) > lthr);
-    const bool b_cond = (sww > 0.f) && gap < A.cond_k * fmaxf(A.a_cov, R(c));
-    bad |= b_lam || b_cond;
-    // a hole itself needs no second opinion: its slope/roughness are NaN by construction (see `inval` below)
-    bad = bad && (fabsf(R(ec)) < 3.0e38f);
-    flag |= bad ? (1u << k) : 0u;
-    if (A.stats) flag |= ((b_inv ? 1u : 0u) | (b_lam ? 2u : 0u) | (b_cond ? 4u : 0u)) << (2 + 4 * k);
+  {
+    const bool ok0 = (min2n(lo(t1), lo(t2)) > 0.f) || (lo(Sww) == 0.f);
+    const bool ok1 = (min2n(hi(t1), hi(t2)) > 0.f) || (hi(Sww) == 0.f);
+    flag = ((!ok0 && lo(inval) == 0.f) ? 1u : 0u) | ((!ok1 && hi(inval) == 0.f) ? 2u : 0u);
   }
-  // where acos amplifies one ulp of n_z beyond the tolerance (theta < ~0.012 rad) certify its rounding
-  const bool cx = smx && lo(s) < 7.2e-5f && lo(Sww) > 0.f, cy = smy && hi(s) < 7.2e-5f && hi(Sww) > 0.f;
-  if (cx || cy) {
-#pragma unroll
-    for (int k = 0; k < 2; ++k) {
-      auto R = [&](f2 v) { return k ? hi(v) : lo(v); };
-      if (!(k ? cy : cx)) continue;
-      const float qv = R(s) * 16777216.0f;
-      const float fr = qv - floorf(qv);
-      // relative error bound of s: the first moments carry <= 2.5e-6*sqrt(Sww) absolute error
-      const float gm2 = fmaf(R(Sk), R(Sk), R(Sl) * R(Sl));
-      const float eps = fmaf(7.1e-6f, sqrt_a(R(Sww) * rcp_a(fmaxf(gm2, 1e-36f))), 2e-6f);
-      if (fabsf(fr - 0.5f) <= fmaf(qv, eps, 1e-3f)) flag |= (1u << k) | (A.stats ? (8u << (2 + 4 * k)) : 0u);
-    }
-  }
+  // where acos amplifies one ulp of n_z beyond the tolerance (theta < ~0.012 rad) certify its float32 rounding
+  if (smx && lo(s) < 7.2e-5f && lo(Sww) > 0.f) flag |= cert_rounding(lo(s), lo(Sk), lo(Sl), lo(Sww)) ? 1u : 0u;
+  if (smy && hi(s) < 7.2e-5f && hi(Sww) > 0.f) flag |= cert_rounding(hi(s), hi(Sk), hi(Sl), hi(Sww)) ? 2u : 0u;
   const f2 theta = acos2(A, nz);
   // layer = x < crit ? 1 - x/crit : 0  ==  max(1 - x/crit, 0)
   const f2 sl = fma2(theta, A.k_minv_slope, A.k_one);
   const f2 ro = fma2(r, A.k_minv_rough, A.k_one);
   // a hole (invalid centre: NaN, or Inf - Inf) has no normal: slope and roughness stay NaN
   // (SlopeFilter.cpp:71, RoughnessFilter.cpp:84) and the cell is not flagged
-  const f2 inval = sub2(ec, ec);
   o.nz = add2(nz, inval);
   o.slope = add2(mk(fmaxf(lo(sl), 0.0f), fmaxf(hi(sl), 0.0f)), inval);
   o.rough = add2(mk(fmaxf(lo(ro), 0.0f), fmaxf(hi(ro), 0.0f)), inval);
@@ -389,14 +387,7 @@ __device__ __forceinline__ Normal2 finish_normal2(const FusedArgs& A, f2 Sw, f2 
 }
 
 // Rare paths kept out of line so that the five unrolled march phases stay small.
-__device__ __noinline__ void append_flagged(unsigned* count, unsigned* list, unsigned cap, int lane, unsigned cell, unsigned fl0, unsigned fl1, unsigned cat) {
-  if (cat >> 2) {
-    const unsigned c0 = (cat >> 2) & 15u, c1 = (cat >> 6) & 15u;
-    const unsigned nl = ((c0 >> 1) & 1u) + ((c1 >> 1) & 1u), nc = ((c0 >> 2) & 1u) + ((c1 >> 2) & 1u), ns = ((c0 >> 3) & 1u) + ((c1 >> 3) & 1u);
-    if (nl) atomicAdd(count + 1, nl);
-    if (nc) atomicAdd(count + 2, nc);
-    if (ns) atomicAdd(count + 3, ns);
-  }
+__device__ __noinline__ void append_flagged(unsigned* count, unsigned* list, unsigned cap, int lane, unsigned cell, unsigned fl0, unsigned fl1) {
   const unsigned b0 = __ballot_sync(FULL, fl0 != 0u), b1 = __ballot_sync(FULL, fl1 != 0u);
   unsigned base = 0;
   if (lane == 0) base = atomicAdd(count, (unsigned)(__popc(b0) + __popc(b1)));
@@ -636,7 +627,7 @@ __device__ __forceinline__ void march_step(StepCtx<S>& C, Lane<S>& L, int t, uns
     // certified slow path: append flagged cells (bit 30: normals part, bit 31: step part)
     const unsigned fl0 = C.out_ok ? ((nf & 1u) | ((sflag & 1u) << 1)) : 0u;
     const unsigned fl1 = C.out_ok ? (((nf >> 1) & 1u) | (sflag & 2u)) : 0u;
-    if (__any_sync(FULL, (fl0 | fl1) != 0u)) append_flagged(A.count, A.list, A.cap, C.lane, (unsigned)C.oc, fl0, fl1, A.stats ? nf : 0u);
+    if (__any_sync(FULL, (fl0 | fl1) != 0u)) append_flagged(A.count, A.list, A.cap, C.lane, (unsigned)C.oc, fl0, fl1);
     C.oc += (size_t)A.rows;
   }
 }
@@ -944,7 +935,6 @@ int launch_chain_fused(FusedState& st, const SlabView& v, const ChainDev& p, int
   double rough_k = 0.06, cond_k = 0.25;
   if (const char* e = std::getenv("TE_FUSED_ROUGH_K")) rough_k = std::atof(e);
   if (const char* e = std::getenv("TE_FUSED_COND_K")) cond_k = std::atof(e);
-  a.stats = std::getenv("TE_FUSED_STATS") != nullptr;
   a.cond_k = (float)cond_k;
   a.rough_thr = (float)((rough_k / p.rough_crit) * (rough_k / p.rough_crit) * (N - 1.0) / N);
   a.kp = (float)(-res / N);
@@ -965,6 +955,7 @@ int launch_chain_fused(FusedState& st, const SlabView& v, const ChainDev& p, int
   a.k_nnm1 = B2(N / (N - 1.0)); a.k_rough_thr = B2((double)a.rough_thr);
   a.k_minv_slope = B2(-1.0 / p.slope_crit); a.k_minv_rough = B2(-1.0 / p.rough_crit);
   a.k_m0 = B2(wn.w[2] >= 0 ? 2 * wn.w[2] + 1 : 0); a.k_m1 = B2(wn.w[1] >= 0 ? 2 * wn.w[1] + 1 : 0);
+  a.k_1em5 = B2(1e-5); a.k_1em10a = B2(1e-10 * (double)a.a_cov); a.k_mcond = B2(-cond_k);
   a.k_one = B2(1.0); a.k_mone = B2(-1.0); a.k_two = B2(2.0); a.k_half = B2(0.5); a.k_mhalf = B2(-0.5); a.k_1p5 = B2(1.5);
   a.k_0375 = B2(0.375); a.k_m03125 = B2(-0.3125);
   a.k_p0 = B2(1.570796251296997); a.k_p1 = B2(-0.21459604799747467); a.k_p2 = B2(0.08894557505846024);
