@@ -75,7 +75,7 @@ struct FusedArgs {
   float cond_k;     // eigen-gap / scale ratio below which the fp32 eigenvector is not trusted
   // constants pre-broadcast to both halves of a register pair (one LDC.64 each)
   f2 k_invN, k_minvN, k_kp, k_half_a, k_nnm1, k_rough_thr, k_minv_slope, k_minv_rough, k_m0, k_m1;
-  f2 k_1em5, k_1em10a, k_mcond;
+  f2 k_1em5, k_1em10a, k_mcond, k_2p24, k_7p1em6, k_2em6, k_1em3;
   f2 k_one, k_mone, k_two, k_half, k_mhalf, k_1p5, k_0375, k_m03125, k_p0, k_p1, k_p2, k_p3, k_p4, k_p5, k_p6, k_p7;
   const unsigned char* rowmask;  // per global row: bit0/1 pass-1 tips (-2,0)/(+2,0); bit2/3 pass-2 tips
   const unsigned char* colmask;  // per global column, same bits for (0,-2)/(0,+2)
@@ -302,16 +302,6 @@ __device__ __forceinline__ float min2n(float a, float b) {
   asm("min.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
   return r;
 }
-// n_z = 1 - s is rounded to float32 with spacing 2^-24: true when s, known to relative error eps, may sit on the other
-// side of a rounding boundary.  eps: the first moments carry <= 2.5e-6*sqrt(Sww) absolute error.  Rare: kept out of line.
-__device__ __noinline__ bool cert_rounding(float s, float sk, float sl, float sww) {
-  const float qv = s * 16777216.0f;
-  const float fr = qv - floorf(qv);
-  const float gm2 = fmaf(sk, sk, sl * sl);
-  const float eps = fmaf(7.1e-6f, sqrt_a(sww * rcp_a(fmaxf(gm2, 1e-36f))), 2e-6f);
-  return fabsf(fr - 0.5f) <= fmaf(qv, eps, 1e-3f);
-}
-
 // Closed-form smallest eigenpair of the scatter matrix [[a,0,p],[0,a,q],[p,q,c]] of a full disk
 // window for both rows of the lane, slope and roughness layers, and the certification of all of it.
 __device__ __forceinline__ Normal2 finish_normal2(const FusedArgs& A, f2 Sw, f2 Sk, f2 Sl, f2 Sww, f2 ec) {
@@ -371,8 +361,20 @@ __device__ __forceinline__ Normal2 finish_normal2(const FusedArgs& A, f2 Sw, f2 
     flag = ((!ok0 && lo(inval) == 0.f) ? 1u : 0u) | ((!ok1 && hi(inval) == 0.f) ? 2u : 0u);
   }
   // where acos amplifies one ulp of n_z beyond the tolerance (theta < ~0.012 rad) certify its float32 rounding
-  if (smx && lo(s) < 7.2e-5f && lo(Sww) > 0.f) flag |= cert_rounding(lo(s), lo(Sk), lo(Sl), lo(Sww)) ? 1u : 0u;
-  if (smy && hi(s) < 7.2e-5f && hi(Sww) > 0.f) flag |= cert_rounding(hi(s), hi(Sk), hi(Sl), hi(Sww)) ? 2u : 0u;
+  // n_z = 1 - s is rounded to float32 with spacing 2^-24: flag when s, known to relative error eps, may sit on the other
+  // side of a rounding boundary (eps: the first moments carry <= 2.5e-6*sqrt(Sww) absolute error).  Both rows at once.
+  const bool cx = smx && lo(s) < 7.2e-5f && lo(Sww) > 0.f, cy = smy && hi(s) < 7.2e-5f && hi(Sww) > 0.f;
+  if (cx || cy) {
+    const f2 qv = mul2(s, A.k_2p24);
+    const f2 fr = sub2(qv, mk(floorf(lo(qv)), floorf(hi(qv))));
+    const f2 gm2 = fma2(Sk, Sk, mul2(Sl, Sl));
+    const f2 ratio = mul2(Sww, mk(rcp_a(fmaxf(lo(gm2), 1e-36f)), rcp_a(fmaxf(hi(gm2), 1e-36f))));
+    const f2 eps = fma2(mk(sqrt_a(lo(ratio)), sqrt_a(hi(ratio))), A.k_7p1em6, A.k_2em6);
+    const f2 bound = fma2(qv, eps, A.k_1em3);
+    const f2 dist = sub2(fr, A.k_half);
+    if (cx && fabsf(lo(dist)) <= lo(bound)) flag |= 1u;
+    if (cy && fabsf(hi(dist)) <= hi(bound)) flag |= 2u;
+  }
   const f2 theta = acos2(A, nz);
   // layer = x < crit ? 1 - x/crit : 0  ==  max(1 - x/crit, 0)
   const f2 sl = fma2(theta, A.k_minv_slope, A.k_one);
@@ -425,7 +427,7 @@ struct StepCtx {
 };
 
 // One march step: column ce = q0 - 4 + t arrives.  PH = t % 5.
-template <class S, int PH>
+template <class S, int PH, bool KN>
 __device__ __forceinline__ void march_step(StepCtx<S>& C, Lane<S>& L, int t, unsigned stage, unsigned cm_js, unsigned cm_jo) {
   const FusedArgs& A = C.A;
   constexpr int S0 = PH, S1 = (PH + 4) % 5, S2 = (PH + 3) % 5, S3 = (PH + 2) % 5, S4 = (PH + 1) % 5;  // slot of age 0..4
@@ -577,7 +579,7 @@ __device__ __forceinline__ void march_step(StepCtx<S>& C, Lane<S>& L, int t, uns
     L.dslope[S0] = n.slope;
     L.drough[S0] = n.rough;
     L.dflag[S0] = n.flag;
-    if (A.nx != nullptr) store_normals(A.nx, A.ny, A.nz, C.out_ok, C.ocn, n.nx, n.ny, n.nz);
+    if constexpr (KN) store_normals(A.nx, A.ny, A.nz, C.out_ok, C.ocn, n.nx, n.ny, n.nz);
     C.ocn += (size_t)A.rows;
   }
   if (t < 8) return;
@@ -632,7 +634,7 @@ __device__ __forceinline__ void march_step(StepCtx<S>& C, Lane<S>& L, int t, uns
   }
 }
 
-template <class S>
+template <class S, bool KN>
 __global__ void TE_KERNEL_ATTR k_chain_fused(const __grid_constant__ CUtensorMap map, FusedArgs A) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int warp = __shfl_sync(FULL, (int)(threadIdx.x >> 5), 0);  // provably warp-uniform: uniform datapath for the control flow
@@ -716,11 +718,11 @@ __global__ void TE_KERNEL_ATTR k_chain_fused(const __grid_constant__ CUtensorMap
           mjs[ph] = mjo[ph] = 0u;
         }
       }
-      march_step<S, 0>(C, L, t0 + 0, st, mjs[0], mjo[0]);
-      march_step<S, 1>(C, L, t0 + 1, st, mjs[1], mjo[1]);
-      march_step<S, 2>(C, L, t0 + 2, st, mjs[2], mjo[2]);
-      march_step<S, 3>(C, L, t0 + 3, st, mjs[3], mjo[3]);
-      march_step<S, 4>(C, L, t0 + 4, st, mjs[4], mjo[4]);
+      march_step<S, 0, KN>(C, L, t0 + 0, st, mjs[0], mjo[0]);
+      march_step<S, 1, KN>(C, L, t0 + 1, st, mjs[1], mjo[1]);
+      march_step<S, 2, KN>(C, L, t0 + 2, st, mjs[2], mjo[2]);
+      march_step<S, 3, KN>(C, L, t0 + 3, st, mjs[3], mjo[3]);
+      march_step<S, 4, KN>(C, L, t0 + 4, st, mjs[4], mjo[4]);
       cm_cur = cm_next;
     }
     kglob += nchunks;
@@ -788,12 +790,12 @@ PFN_encodeTiled get_encode() {
   return fn;
 }
 
-template <class S>
+template <class S, bool KN>
 int launch_shape(FusedState& st, const CUtensorMap& map, const FusedArgs& a, int sms, cudaStream_t s) {
   static bool attr_set = false;
   const int smem = WARPS_PER_CTA * WARP_SMEM_BYTES;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(k_chain_fused<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
+    if (cudaFuncSetAttribute(k_chain_fused<S, KN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
       st.why = "cudaFuncSetAttribute(max dynamic shared memory) failed";
       return 1;
     }
@@ -802,7 +804,7 @@ int launch_shape(FusedState& st, const CUtensorMap& map, const FusedArgs& a, int
   const int nunits = a.nstrips * a.nseg * a.nmaps;
   int grid = std::min(sms, (nunits + WARPS_PER_CTA - 1) / WARPS_PER_CTA);
   if (grid < 1) grid = 1;
-  k_chain_fused<S><<<grid, WARPS_PER_CTA * 32, smem, s>>>(map, a);
+  k_chain_fused<S, KN><<<grid, WARPS_PER_CTA * 32, smem, s>>>(map, a);
   return 0;
 }
 
@@ -956,6 +958,7 @@ int launch_chain_fused(FusedState& st, const SlabView& v, const ChainDev& p, int
   a.k_minv_slope = B2(-1.0 / p.slope_crit); a.k_minv_rough = B2(-1.0 / p.rough_crit);
   a.k_m0 = B2(wn.w[2] >= 0 ? 2 * wn.w[2] + 1 : 0); a.k_m1 = B2(wn.w[1] >= 0 ? 2 * wn.w[1] + 1 : 0);
   a.k_1em5 = B2(1e-5); a.k_1em10a = B2(1e-10 * (double)a.a_cov); a.k_mcond = B2(-cond_k);
+  a.k_2p24 = B2(16777216.0); a.k_7p1em6 = B2(7.1e-6); a.k_2em6 = B2(2e-6); a.k_1em3 = B2(1e-3);
   a.k_one = B2(1.0); a.k_mone = B2(-1.0); a.k_two = B2(2.0); a.k_half = B2(0.5); a.k_mhalf = B2(-0.5); a.k_1p5 = B2(1.5);
   a.k_0375 = B2(0.375); a.k_m03125 = B2(-0.3125);
   a.k_p0 = B2(1.570796251296997); a.k_p1 = B2(-0.21459604799747467); a.k_p2 = B2(0.08894557505846024);
@@ -967,8 +970,8 @@ int launch_chain_fused(FusedState& st, const SlabView& v, const ChainDev& p, int
   a.nx = (o.nx && o.ny && o.nz) ? o.nx : nullptr; a.ny = o.ny; a.nz = o.nz;
   a.list = list; a.count = count; a.cap = cap;
   switch (st.shape_id) {
-    case 0: return launch_shape<ShapeA>(st, map, a, sms, s);
-    case 1: return launch_shape<ShapeB>(st, map, a, sms, s);
+    case 0: return a.nx ? launch_shape<ShapeA, true>(st, map, a, sms, s) : launch_shape<ShapeA, false>(st, map, a, sms, s);
+    case 1: return a.nx ? launch_shape<ShapeB, true>(st, map, a, sms, s) : launch_shape<ShapeB, false>(st, map, a, sms, s);
   }
   st.why = "unknown shape id";
   return 1;
