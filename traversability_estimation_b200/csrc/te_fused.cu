@@ -389,7 +389,8 @@ __device__ __forceinline__ Normal2 finish_normal2(const FusedArgs& A, f2 Sw, f2 
 }
 
 // Rare paths kept out of line so that the five unrolled march phases stay small.
-__device__ __noinline__ void append_flagged(unsigned* count, unsigned* list, unsigned cap, int lane, unsigned cell, unsigned fl0, unsigned fl1) {
+__device__ __noinline__ void append_flagged(unsigned* count, unsigned* list, unsigned cap, int lane, unsigned cell, unsigned fl) {
+  const unsigned fl0 = (fl & 1u) | ((fl >> 1) & 2u), fl1 = ((fl >> 1) & 1u) | ((fl >> 2) & 2u);  // per row: bit0 normals, bit1 step
   const unsigned b0 = __ballot_sync(FULL, fl0 != 0u), b1 = __ballot_sync(FULL, fl1 != 0u);
   unsigned base = 0;
   if (lane == 0) base = atomicAdd(count, (unsigned)(__popc(b0) + __popc(b1)));
@@ -613,7 +614,7 @@ __device__ __forceinline__ void march_step(StepCtx<S>& C, Lane<S>& L, int t, uns
       const float stepMax = fmaxf(mx, 0.0f);
       const float st = fminf(stepMax, cnt * A.inv_ncrit * stepMax);
       // st < crit ? 1 - st/crit : 0 ; no finite step_height in the window (mx is NaN) -> layer stays NaN (StepFilter.cpp:169)
-      outv[r] = (mx == mx) ? fmaxf(fmaf(-st, A.inv_step_crit, 1.0f), 0.0f) : mx;
+      outv[r] = fmaxf(fmaf(-st, A.inv_step_crit, 1.0f), 0.0f) + (mx - mx);  // mx NaN (or Inf - Inf) keeps the layer NaN
     }
     const f2 sl = L.dslope[S2], ro = L.drough[S2];
     const unsigned nf = L.dflag[S2];
@@ -627,9 +628,8 @@ __device__ __forceinline__ void march_step(StepCtx<S>& C, Lane<S>& L, int t, uns
       *reinterpret_cast<float2*>(A.trav + oc) = make_float2(t0, t1);
     }
     // certified slow path: append flagged cells (bit 30: normals part, bit 31: step part)
-    const unsigned fl0 = C.out_ok ? ((nf & 1u) | ((sflag & 1u) << 1)) : 0u;
-    const unsigned fl1 = C.out_ok ? (((nf >> 1) & 1u) | (sflag & 2u)) : 0u;
-    if (__any_sync(FULL, (fl0 | fl1) != 0u)) append_flagged(A.count, A.list, A.cap, C.lane, (unsigned)C.oc, fl0, fl1);
+    const unsigned fl = C.out_ok ? (nf | (sflag << 2)) : 0u;  // bits 0/1: normals part of row x/y, bits 2/3: step part
+    if (__any_sync(FULL, fl != 0u)) append_flagged(A.count, A.list, A.cap, C.lane, (unsigned)C.oc, fl);
     C.oc += (size_t)A.rows;
   }
 }
