@@ -84,24 +84,36 @@ __device__ bool normals_t2(const FixupArgs& A, const Elev& E, int i, int j, floa
     fnx = fny = fnz = slope = rough = nanf_();
     return true;
   }
-  // gather the 5 x 5 neighbourhood once (25 independent loads), then work from registers
+  // gather the 5 x 5 neighbourhood with 25 unconditional, independent loads (indices clamped into the buffer; what lies
+  // outside the map / window / buffer is masked to NaN afterwards), then work from registers without branches
   float zw[5][5];
+  {
+    const int lb0 = j - A.in_col0;
 #pragma unroll
-  for (int l = -2; l <= 2; ++l)
-#pragma unroll
-    for (int k = -2; k <= 2; ++k) {
+    for (int l = -2; l <= 2; ++l) {
+      const int b = j + l, lb = lb0 + l;
+      const bool col_ok = b >= 0 && b < A.cols_total && lb >= 0 && lb < A.in_ncols;
+      const float* col = E.e + (size_t)min(max(lb, 0), A.in_ncols - 1) * A.rows;
       const int w = A.wn[l < 0 ? -l : l];
-      zw[l + 2][k + 2] = (k >= -w && k <= w) ? E(i + k, j + l) : nanf_();
+#pragma unroll
+      for (int k = -2; k <= 2; ++k) {
+        const int a = i + k;
+        const float v = __ldg(col + min(max(a, 0), A.rows - 1));
+        const bool ok = col_ok && a >= 0 && a < A.rows && k >= -w && k <= w && finitef(v);
+        zw[l + 2][k + 2] = ok ? v : nanf_();
+      }
     }
+  }
   double n = 0, su = 0, sv = 0, sw = 0, suu = 0, suv = 0, svv = 0, suw = 0, svw = 0, sww = 0;
 #pragma unroll
   for (int l = -2; l <= 2; ++l)
 #pragma unroll
     for (int k = -2; k <= 2; ++k) {
       const float z = zw[l + 2][k + 2];
-      if (!finitef(z)) continue;
-      const double u = -A.res * (double)k, v = -A.res * (double)l, d = (double)z - (double)zc;
-      n += 1.0; su += u; sv += v; sw += d;
+      const bool ok = finitef(z);
+      const double m = ok ? 1.0 : 0.0;                       // invalid cells contribute exact zeros
+      const double u = m * (-A.res * (double)k), v = m * (-A.res * (double)l), d = ok ? (double)z - (double)zc : 0.0;
+      n += m; su += u; sv += v; sw += d;
       suu += u * u; suv += u * v; svv += v * v; suw += u * d; svw += v * d; sww += d * d;
     }
   double nx = 0.0, ny = 0.0, nz = 1.0;
@@ -178,17 +190,17 @@ __device__ bool normals_t2(const FixupArgs& A, const Elev& E, int i, int j, floa
   slope = (float)(th < A.slope_crit ? 1.0 - th / A.slope_crit : 0.0);
   // roughness with the float32 normal (RoughnessFilter.cpp:108-117)
   const double NX = fnx, NY = fny, NZ = fnz;
-  double sum = 0.0, cnt = 0.0;
+  double sum = 0.0;
+  const double cnt = n;
   const double plane = mu * NX + mv * NY + mw * NZ;
 #pragma unroll
   for (int l = -2; l <= 2; ++l)
 #pragma unroll
     for (int k = -2; k <= 2; ++k) {
       const float z = zw[l + 2][k + 2];
-      if (!finitef(z)) continue;
+      const bool ok = finitef(z);
       const double d = NX * (-A.res * (double)k) + NY * (-A.res * (double)l) + NZ * ((double)z - (double)zc) - plane;
-      sum += d * d;
-      cnt += 1.0;
+      sum += ok ? d * d : 0.0;
     }
   const double r = sqrt(sum / (cnt - 1.0));  // one point: 0/0 = NaN -> comparison false -> 0.0
   rough = (float)(r < A.rough_crit ? 1.0 - r / A.rough_crit : 0.0);

@@ -320,13 +320,23 @@ __device__ void chain_cell_literal(const SlabView& v, const ChainDev& p, const f
     if (use_window && p.Rn <= 3 && p.Rr <= 3) {
       ElevWindow Wn;
       Wn.fill(E, i, j);
+      // the coordinates of the neighbourhood too: the window loops then run on local data only
+      double Xl[7], Yl[7];
+#pragma unroll
+      for (int k = 0; k < 7; ++k) {
+        Xl[k] = v.X[min(max(i - 3 + k, 0), v.rows - 1)];
+        Yl[k] = v.Y[min(max(j - 3 + k, 0), v.cols_total - 1)];
+      }
+      SlabView vl = v;
+      vl.X = Xl - (i - 3);
+      vl.Y = Yl - (j - 3);
       if (finitef(Wn(i, j))) {
         double n[3];
-        normal_literal(v, p, Wn, i, j, n);
+        normal_literal(vl, p, Wn, i, j, n);
         fnx = (float)n[0]; fny = (float)n[1]; fnz = (float)n[2];
       }
       s = slope_literal(fnz, p.slope_crit);
-      r = roughness_literal(v, p, Wn, i, j, fnx, fny, fnz);
+      r = roughness_literal(vl, p, Wn, i, j, fnx, fny, fnz);
     } else {
       if (finitef(E(i, j))) {
         double n[3];
