@@ -190,12 +190,12 @@ def run_reference(args):
     z = synth.terrain(n, n, RES, seed=3, preset="mixed", holes=args.holes)
     g = ob.Geometry.make(n, n, RES)
     p = ob.ChainParams.yaml_defaults(0)
-    threads = ob.max_threads()
+    threads = len(os.sched_getaffinity(0))  # all host threads, also under torchrun (which exports OMP_NUM_THREADS=1)
     for _ in range(args.warmup):
-        ob.chain(g, p, z)
+        ob.chain(g, p, z, nthreads=threads)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        ob.chain(g, p, z)
+        ob.chain(g, p, z, nthreads=threads)
     dt = time.perf_counter() - t0
     val = n * n * args.steps / dt / 1e6
     out = {"impl": "reference", "metric": "Mcells/s full filter chain, synthetic elevation", "value": val, "unit": "Mcells/s",
@@ -418,10 +418,10 @@ def main():
         crop = np.asfortranarray(own[:n, :n].cpu().numpy().T)
         og = ob.Geometry.make(n, n, RES)
         op = ob.ChainParams.yaml_defaults(0)
-        threads = ob.max_threads()
-        ob.chain(ob.Geometry.make(128, 128, RES), op, np.asfortranarray(crop[:128, :128]))  # warm the thread pool
+        threads = len(os.sched_getaffinity(0))
+        ob.chain(ob.Geometry.make(128, 128, RES), op, np.asfortranarray(crop[:128, :128]), nthreads=threads)  # warm the thread pool
         t0 = time.perf_counter()
-        ob.chain(og, op, crop)
+        ob.chain(og, op, crop, nthreads=threads)
         dt = time.perf_counter() - t0
         cpu = {"value": n * n / dt / 1e6, "unit": "Mcells/s", "cores": threads, "kind": "port",
                "sample": f"{n}x{n} crop of the same map, one pass, OpenMP over {threads} host threads "
