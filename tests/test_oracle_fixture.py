@@ -52,3 +52,19 @@ def test_single_filters_compose_to_chain(oracle, fixture_map):
     assert np.all(nz >= 0)
     nrm = nx.astype(np.float64) ** 2 + ny.astype(np.float64) ** 2 + nz.astype(np.float64) ** 2
     assert np.allclose(nrm, 1.0, atol=1e-6)
+
+
+def test_golden_vectors_can_be_regenerated_from_the_reference_bag(fixture_map):
+    """Only where the reference checkout exists (the build container): tests/golden/ equals a fresh decode of the bag."""
+    import os
+    import pytest
+    bag = "/root/reference/traversability_estimation/maps/elevation_map.bag"
+    if not os.path.exists(bag):
+        pytest.skip("reference checkout not present (GPU box)")
+    from bag import read_gridmap_bag
+    m, d = fixture_map
+    msg = read_gridmap_bag(bag)
+    assert (msg.rows, msg.cols, msg.resolution) == (m["rows"], m["cols"], m["resolution"])
+    assert msg.outer_start_index == 0 and msg.inner_start_index == 0
+    for k, v in d.items():
+        assert np.array_equal(msg.data[k].view(np.uint32), v.view(np.uint32)), k
