@@ -50,6 +50,8 @@ struct FpArgs {
   const double* P;            // per input-buffer column: rows+1 prefix sums of t' along the row index
   const unsigned* bits;       // per input-buffer column: (rows+31)/32 words of blocked flags
   int words;                  // words per column
+  const unsigned char* near;  // per input-buffer cell: distance (rows) to the nearest blocked cell of its column, 255 = none within 31
+  signed char halfw_c[64];    // copy of `halfw` in the kernel parameters (constant bank)
 };
 
 __device__ __forceinline__ float lay(const FpArgs& A, const float* l, int i, int j) {  // caller guarantees (i,j) is in the map
@@ -314,6 +316,29 @@ __global__ void __launch_bounds__(256) k_fp_prepare(FpArgs A, Layers L, const un
   }
 }
 
+// Distance along the row index from every cell to the nearest blocked cell of its own column (from the packed flags):
+// the sweep then needs ONE byte per disk column to know the nearest blocked cell of that column.
+__global__ void __launch_bounds__(256) k_fp_nearest(FpArgs A, unsigned char* __restrict__ near) {
+  const long long total = (long long)A.rows * A.in_ncols;
+  for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < total; c += (long long)gridDim.x * blockDim.x) {
+    const int i = (int)(c % A.rows);
+    const int lb = (int)(c / A.rows);
+    const unsigned* wcol = A.bits + (size_t)lb * A.words;
+    const int r0 = i - 31, w0 = r0 >> 5, sh = r0 & 31;
+    const unsigned a0 = (w0 >= 0 && w0 < A.words) ? __ldg(wcol + w0) : 0u;
+    const unsigned a1 = (w0 + 1 >= 0 && w0 + 1 < A.words) ? __ldg(wcol + w0 + 1) : 0u;
+    const unsigned a2 = (w0 + 2 >= 0 && w0 + 2 < A.words) ? __ldg(wcol + w0 + 2) : 0u;
+    const unsigned long long lo = ((unsigned long long)a1 << 32) | a0;
+    unsigned long long f = (lo >> sh) | (sh ? ((unsigned long long)a2 << (64 - sh)) : 0ull);  // bit t <-> row r0 + t, centre at bit 31
+    f &= ~(1ull << 63);                                                                        // rows i-31 .. i+31
+    int kmin = 255;
+    const unsigned long long up = f >> 31, dn = f & ((1ull << 31) - 1ull);
+    if (up) kmin = __ffsll((long long)up) - 1;
+    if (dn) kmin = min(kmin, 31 - (63 - __clzll((long long)dn)));
+    near[c] = (unsigned char)kmin;
+  }
+}
+
 // isTraversable for every cell on prefix sums: the visited set is a lattice disk, so "is anything blocked in it"
 // and "sum / count of the visited cells" are 2L+1 column queries instead of ~pi r^2 visits; only when a blocker
 // exists is the ring that holds the first one walked in SpiralIterator order.
@@ -326,32 +351,15 @@ __global__ void __launch_bounds__(256) k_sweep_fast(FpArgs A, Layers L, const un
     const double cx = A.X[i], cy = A.Y[j];
     // ---- nearest blocked cell of the visited set, as a squared index distance ------------------------
     int best = 0x7fffffff;
-    const int r0 = i - 31;                      // window of 64 rows [r0, r0+64) around the centre (needs L <= 31)
-    const int w0 = r0 >> 5, sh = r0 & 31;       // arithmetic shift: rows < 0 live in words < 0
-    for (int l = -A.L; l <= A.L; ++l) {
-      const int b = j + l, lb = b - A.in_col0;
-      const int hw = A.halfw[l + A.L];
-      if (hw < 0 || b < 0 || b >= A.cols_total || lb < 0 || lb >= A.in_ncols) continue;
-      const unsigned* wcol = A.bits + (size_t)lb * A.words;
-      unsigned long long lo = 0ull, hi = 0ull;
-      {
-        const unsigned a0 = (w0 >= 0 && w0 < A.words) ? __ldg(wcol + w0) : 0u;
-        const unsigned a1 = (w0 + 1 >= 0 && w0 + 1 < A.words) ? __ldg(wcol + w0 + 1) : 0u;
-        const unsigned a2 = (w0 + 2 >= 0 && w0 + 2 < A.words) ? __ldg(wcol + w0 + 2) : 0u;
-        lo = ((unsigned long long)a1 << 32) | a0;
-        hi = a2;
+    // disk columns that exist in the map and in this slab's buffer
+    const int l_lo = max(-A.L, max(-j, A.in_col0 - j)), l_hi = min(A.L, min(A.cols_total - 1 - j, A.in_col0 + A.in_ncols - 1 - j));
+    {
+      const unsigned char* nr = A.near + (size_t)(j + l_lo - A.in_col0) * A.rows + i;
+      for (int l = l_lo; l <= l_hi; ++l, nr += A.rows) {
+        const int g = (int)__ldg(nr);              // nearest blocked row offset in this column
+        const int hw = A.halfw_c[l + A.L];
+        if (g <= hw) best = min(best, g * g + l * l);
       }
-      unsigned long long f = (lo >> sh) | (sh ? (hi << (64 - sh)) : 0ull);  // bit t <-> row r0 + t ; centre at bit 31
-      // keep rows i-hw .. i+hw
-      const unsigned long long m = ((1ull << (2 * hw + 1)) - 1ull) << (31 - hw);  // hw <= 31
-      f &= m;
-      if (!f) continue;
-      const unsigned long long up = f >> 31;                  // k >= 0 at bit k
-      const unsigned long long dn = f & ((1ull << 31) - 1ull); // k < 0: row i+k at bit 31+k
-      int kmin = 64;
-      if (up) kmin = __ffsll((long long)up) - 1;
-      if (dn) kmin = min(kmin, 31 - (63 - __clzll((long long)dn)));
-      best = min(best, kmin * kmin + l * l);
     }
     for (int q = 0; q < A.n_fuzzy; ++q) {
       const int w = A.fuzzy[q];
@@ -366,16 +374,32 @@ __global__ void __launch_bounds__(256) k_sweep_fast(FpArgs A, Layers L, const un
     const bool any = best != 0x7fffffff;
     const int dstar = any ? (int)sqrt((double)best) : A.nrings + 1;  // ring of the first blocked cell
     const signed char* hwt = any ? (A.inner + (size_t)dstar * W) : A.halfw;
-    double t = 0.0;
+    double t = 0.0, t_b = 0.0;
     int n = 0;
-    for (int l = -A.L; l <= A.L; ++l) {
-      const int b = j + l, lb = b - A.in_col0;
-      const int hw = hwt[l + A.L];
-      if (hw < 0 || b < 0 || b >= A.cols_total || lb < 0 || lb >= A.in_ncols) continue;
-      const int a0 = max(i - hw, 0), a1 = min(i + hw, A.rows - 1);
-      const double* pcol = A.P + (size_t)lb * (A.rows + 1);
-      t += pcol[a1 + 1] - pcol[a0];
-      n += a1 - a0 + 1;
+    {
+      const double* pc = A.P + (size_t)(j + l_lo - A.in_col0) * (A.rows + 1);
+      const size_t pstride = (size_t)A.rows + 1;
+      if (i - A.L >= 0 && i + A.L < A.rows) {  // no clipping along the rows: two independent accumulators
+        int l = l_lo;
+        for (; l + 1 <= l_hi; l += 2, pc += 2 * pstride) {
+          const int h0 = hwt[l + A.L], h1 = hwt[l + 1 + A.L];
+          if (h0 >= 0) { t += pc[i + h0 + 1] - pc[i - h0]; n += 2 * h0 + 1; }
+          if (h1 >= 0) { t_b += pc[pstride + i + h1 + 1] - pc[pstride + i - h1]; n += 2 * h1 + 1; }
+        }
+        if (l <= l_hi) {
+          const int h0 = hwt[l + A.L];
+          if (h0 >= 0) { t += pc[i + h0 + 1] - pc[i - h0]; n += 2 * h0 + 1; }
+        }
+      } else {
+        for (int l = l_lo; l <= l_hi; ++l, pc += pstride) {
+          const int hw = hwt[l + A.L];
+          if (hw < 0) continue;
+          const int a0 = max(i - hw, 0), a1 = min(i + hw, A.rows - 1);
+          t += pc[a1 + 1] - pc[a0];
+          n += a1 - a0 + 1;
+        }
+      }
+      t += t_b;
     }
     float result;
     if (!any) {
@@ -577,18 +601,21 @@ int launch_footprint(FootprintState& st, const SlabView& v, const te_geometry* g
     st.off_halfw = put(halfw.data(), halfw.size(), 1);
     st.off_inner = put(inner.data(), inner.size(), 1);
     if (cudaStreamSynchronize(s) != cudaSuccess) { st.why = "footprint table upload failed"; return TE_ERR_CUDA; }
+    std::memset(st.h_halfw, -1, sizeof(st.h_halfw));
+    std::memcpy(st.h_halfw, halfw.data(), std::min(halfw.size(), sizeof(st.h_halfw)));
     st.n_fuzzy = (int)fuzzy.size();
     st.L = Lmax;
     st.nrings = nR;
     st.tables_valid = true;
   }
   const int words = (v.rows + 31) / 32;
-  const size_t pbytes = sizeof(double) * (size_t)(v.rows + 1) * v.in_ncols, wbytes = sizeof(unsigned) * (size_t)words * v.in_ncols;
-  if (st.prefix_cap < pbytes + wbytes) {
+  const size_t pbytes = sizeof(double) * (size_t)(v.rows + 1) * v.in_ncols, wbytes = (sizeof(unsigned) * (size_t)words * v.in_ncols + 15) / 16 * 16;
+  const size_t gbytes = ncell_in;
+  if (st.prefix_cap < pbytes + wbytes + gbytes) {
     if (st.d_prefix) cudaFree(st.d_prefix);
     st.d_prefix = nullptr; st.prefix_cap = 0;
-    if (cudaMalloc(&st.d_prefix, pbytes + wbytes) != cudaSuccess) { st.why = "cudaMalloc(footprint prefix sums) failed"; return TE_ERR_CUDA; }
-    st.prefix_cap = pbytes + wbytes;
+    if (cudaMalloc(&st.d_prefix, pbytes + wbytes + gbytes) != cudaSuccess) { st.why = "cudaMalloc(footprint prefix sums) failed"; return TE_ERR_CUDA; }
+    st.prefix_cap = pbytes + wbytes + gbytes;
   }
   a.L = st.L; a.nrings = st.nrings; a.n_fuzzy = st.n_fuzzy; a.words = words;
   a.ring_start = (const int*)((char*)st.d_tables + st.off_ring);
@@ -597,10 +624,14 @@ int launch_footprint(FootprintState& st, const SlabView& v, const te_geometry* g
   a.inner = (const signed char*)((char*)st.d_tables + st.off_inner);
   a.P = (const double*)st.d_prefix;
   a.bits = (const unsigned*)((char*)st.d_prefix + pbytes);
+  a.near = (const unsigned char*)st.d_prefix + pbytes + wbytes;
+  std::memcpy(a.halfw_c, st.h_halfw, sizeof(a.halfw_c));
   const int g3 = std::min(sms * 8, (v.in_ncols + 7) / 8);
+  const int g1b = (int)std::min<long long>((t1 + 255) / 256, (long long)sms * 8);
   k_fp_prepare<<<std::max(g3, 1), 256, 0, s>>>(a, L, (const unsigned char*)st.d_block, (double*)st.d_prefix, (unsigned*)((char*)st.d_prefix + pbytes));
+  k_fp_nearest<<<std::max(g1b, 1), 256, 0, s>>>(a, (unsigned char*)st.d_prefix + pbytes + wbytes);
   k_sweep_fast<<<std::max(g2, 1), 256, 0, s>>>(a, L, (const unsigned char*)st.d_block, out);
-  if (launches) *launches = 3;
+  if (launches) *launches = 4;
   return 0;
 }
 

@@ -24,6 +24,7 @@ struct FootprintState {
   bool tables_valid = false;
   size_t off_ring = 0, off_fuzzy = 0, off_halfw = 0, off_inner = 0;
   int n_fuzzy = 0, L = 0, nrings = 0;
+  signed char h_halfw[64] = {0};
   void* d_prefix = nullptr;
   size_t prefix_cap = 0;
   void invalidate() { valid = false; tables_valid = false; }
