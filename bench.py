@@ -41,7 +41,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="chain8192", choices=["chain8192", "chain2048", "batched512", "footprint4096"])
+    ap.add_argument("--workload", default="chain8192", choices=["chain8192", "chain2048", "batched512", "footprint4096", "slope8192"])
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--kernel", default="auto", choices=["auto", "generic", "fused"])
     ap.add_argument("--holes", type=float, default=0.01, help="fraction of NaN cells (blobs)")
@@ -231,6 +231,17 @@ def run_other(args, torch, dist, te, world, rank, local, dev):
 
         def step():
             ctx.chain_batched(g, prm, n, z, *outs, te.MEM_DEVICE)
+    elif args.workload == "slope8192":
+        rows = cols = args.rows or 8192
+        assert world == 1
+        g = te.Geometry.make(rows, cols, RES)
+        nz = torch.rand((cols, rows), dtype=torch.float32, device=dev) * 0.5 + 0.5
+        out = torch.empty_like(nz)
+        cells = rows * cols
+        name = f"SlopeFilter only (te_slope) over a {rows}x{cols} surface_normal_z layer, 8 B/cell"
+
+        def step():
+            ctx.slope(g, 1.0, nz, out, te.MEM_DEVICE)
     else:
         rows = cols = args.rows or 4096
         assert world == 1, "footprint bench is single-GPU"
@@ -268,14 +279,15 @@ def run_other(args, torch, dist, te, world, rank, local, dev):
     l1, _ = ctx.stats()
     if rank == 0:
         peak, src = measured_peak()
-        ach = ALG_BYTES_PER_CELL * (cells / world) / (ms / args.steps * 1e-3) / 1e9
-        print(json.dumps({"metric": "Mcells/s " + ("full filter chain" if args.workload == "batched512" else "footprint sweep") + ", synthetic elevation",
+        bpc = 8 if args.workload == "slope8192" else ALG_BYTES_PER_CELL
+        ach = bpc * (cells / world) / (ms / args.steps * 1e-3) / 1e9
+        print(json.dumps({"metric": "Mcells/s " + {"batched512": "full filter chain", "slope8192": "slope filter"}.get(args.workload, "footprint sweep") + ", synthetic elevation",
                           "value": cells * args.steps / (ms * 1e-3) / 1e6, "unit": "Mcells/s", "n_gpus": world, "steps": args.steps,
                           "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
                           "vs_baseline": None, "dtype": "f32 (f64 certified slow path)" if args.workload == "batched512" else "f64/f32", "data": "synthetic",
                           "config": {"workload": name, "holes": args.holes},
                           "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
-                                       "peak_source": src, "note": "whole step (all kernels of the pass), 20 B/cell"},
+                                       "peak_source": src, "note": "whole step (all kernels of the pass), %d B/cell" % bpc},
                           "cpu_baseline": None, "e2e": None, "gpu_launches": int(l1 - l0), "clocks": None}))
     if world > 1:
         dist.destroy_process_group()
@@ -302,7 +314,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     assert world == args.gpus or world == 1, (world, args.gpus)
 
-    if args.workload in ("batched512", "footprint4096"):
+    if args.workload in ("batched512", "footprint4096", "slope8192"):
         return run_other(args, torch, dist, te, world, rank, local, dev)
     rows = args.rows or {"chain8192": 8192, "chain2048": 2048}.get(args.workload, 8192)
     base_cols = args.cols or rows
