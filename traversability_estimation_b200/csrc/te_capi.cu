@@ -242,11 +242,11 @@ int run_chain_device(te_ctx* c, const te_geometry* g, const te::SlabView& v, con
     const unsigned cap = (unsigned)std::min<size_t>(out_stride * (size_t)nmaps, (size_t)1 << 26);
     TE_CUDA(c->worklist.reserve(sizeof(unsigned) * (size_t)cap));
     TE_CUDA(c->worklist3.reserve(sizeof(unsigned) * (size_t)cap));
-    TE_CUDA(c->counter.reserve(sizeof(unsigned) * 8));
+    TE_CUDA(c->counter.reserve(sizeof(unsigned) * 64));
     {  // one launch covers every map of the batch
       const te::ChainOut& om = o;
       const int m = 0;
-      TE_CUDA(cudaMemsetAsync(c->counter.p, 0, sizeof(unsigned) * 8, c->stream));
+      TE_CUDA(cudaMemsetAsync(c->counter.p, 0, sizeof(unsigned) * 64, c->stream));
       te_ctx::Ev3 ev{};
       if (c->timing) {
         TE_CUDA(cudaEventCreate(&ev.a)); TE_CUDA(cudaEventCreate(&ev.b)); TE_CUDA(cudaEventCreate(&ev.c));

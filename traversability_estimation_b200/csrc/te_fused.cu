@@ -54,12 +54,21 @@ constexpr int WARPS_PER_CTA = TE_WPC;
 #endif
 constexpr unsigned FULL = 0xffffffffu;
 
+constexpr int NLVL = 4;            // levels of the work queue
+
 typedef unsigned long long f2;  // two packed floats in one aligned register pair (see below)
 
 struct FusedArgs {
   int rows, cols_total;
   int in_col0, in_ncols, out_col0, out_ncols;
-  int nstrips, nseg, seg_len;
+  int nstrips;
+  // work queue: units are (level, map, column segment, strip); levels hold ever shorter segments so the
+  // warps that pop the queue last finish close together
+  int lvl_unit0[NLVL + 1];      // first unit of each level; [NLVL] = number of units
+  int lvl_col0[NLVL + 1];       // first output column (relative to out_col0) of each level
+  int lvl_len[NLVL];            // segment length of each level
+  int lvl_nseg[NLVL];           // segments per map of each level
+  unsigned* queue;              // zeroed before the launch; warps pop unit ids past their first one
   int nmaps;                    // independent maps stored back to back (te_chain_batched); 1 otherwise
   unsigned map_cells;           // rows * out_ncols: output cells per map
   float half_a;     // 0.5 * res^2 * K2 / N   (Cxx = Cyy of a full window is a = 2*half_a)
@@ -75,6 +84,7 @@ struct FusedArgs {
   float cond_k;     // eigen-gap / scale ratio below which the fp32 eigenvector is not trusted
   // constants pre-broadcast to both halves of a register pair (one LDC.64 each)
   f2 k_invN, k_minvN, k_kp, k_half_a, k_nnm1, k_rough_thr, k_minv_slope, k_minv_rough, k_m0, k_m1;
+  f2 k_inv_ncrit, k_minv_step, k_fuse_w;
   f2 k_1em5, k_1em10a, k_mcond, k_2p24, k_7p1em6, k_2em6, k_1em3;
   f2 k_one, k_mone, k_two, k_half, k_mhalf, k_1p5, k_0375, k_m03125, k_p0, k_p1, k_p2, k_p3, k_p4, k_p5, k_p6, k_p7;
   const unsigned char* rowmask;  // per global row: bit0/1 pass-1 tips (-2,0)/(+2,0); bit2/3 pass-2 tips
@@ -180,6 +190,9 @@ __device__ __forceinline__ f2 lds64(unsigned a) {
 }
 __device__ __forceinline__ void sts64(unsigned a, float x, float y) {
   asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(a), "f"(x), "f"(y) : "memory");
+}
+__device__ __forceinline__ void sts64(unsigned a, f2 v) {
+  asm volatile("st.shared.b64 [%0], %1;" ::"r"(a), "l"(v) : "memory");
 }
 __device__ __forceinline__ void mbar_init(unsigned bar, int count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
@@ -486,7 +499,7 @@ __device__ __forceinline__ void march_step(StepCtx<S>& C, Lane<S>& L, int t, uns
   // ---- stage B: step_height of column js = ce - 2 (ages: js+1 -> 1, js -> 2, js-1 -> 3) ---------
   const unsigned shcol = C.sh_lane + (t & 1) * SHBUF_BYTES;
   {
-    float shv[2];
+    float mn2[2], mx2[2];
     f2 TL1 = L.e[S4], TR1 = L.e[S0];
     if constexpr (S::TIP1) {
       const float qn = __int_as_float(0x7fc00000);
@@ -506,11 +519,12 @@ __device__ __forceinline__ void march_step(StepCtx<S>& C, Lane<S>& L, int t, uns
         mn = min3n(mn, tl, tr);
         mx = max3n(mx, tl, tr);
       }
-      // centre gate (StepFilter.cpp:113): an invalid centre (NaN, or Inf: Inf - Inf) leaves step_height NaN
-      const float zc = R(L.e[S2]);
-      shv[r] = (mx - mn) + (zc - zc);
+      mn2[r] = mn;
+      mx2[r] = mx;
     }
-    sts64(shcol + 8, shv[0], shv[1]);  // buffer row 0 is strip row -2
+    // centre gate (StepFilter.cpp:113): an invalid centre (NaN, or Inf: Inf - Inf) leaves step_height NaN
+    const f2 zc = L.e[S2];
+    sts64(shcol + 8, add2(sub2(mk(mx2[0], mx2[1]), mk(mn2[0], mn2[1])), sub2(zc, zc)));  // buffer row 0 is strip row -2
   }
   __syncwarp();
   float v[6], f[6];
@@ -525,29 +539,33 @@ __device__ __forceinline__ void march_step(StepCtx<S>& C, Lane<S>& L, int t, uns
     for (int k = 0; k < 6; ++k) f[k] = gtf(v[k], A.step_crit);
   }
   {
-    float smx[2], pmx[2], sc[2], pc[2];
+    float smx[2], pmx[2], sc[2];
+    const float fmid = f[2] + f[3];
+    const float c3[2] = {f[1] + fmid, fmid + f[4]};  // counts are small integers: any association is exact
+    f2 PC = mk(c3[0], c3[1]);
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
       const float hi3 = max3n(v[r + 1], v[r + 2], v[r + 3]);
-      const float c3 = f[r + 1] + f[r + 2] + f[r + 3];
-      if constexpr (S::W21 == 1) { smx[r] = hi3; sc[r] = c3; }
+      if constexpr (S::W21 == 1) { smx[r] = hi3; sc[r] = c3[r]; }
       else if constexpr (S::W21 >= 0) { smx[r] = colmax_w<(S::W21 < 0 ? 0 : S::W21)>(v, r); sc[r] = colcnt_w<(S::W21 < 0 ? 0 : S::W21)>(f, r); }
       else { smx[r] = 0.f; sc[r] = 0.f; }
-      float mx = hi3, cnt = c3;
+      float mx = hi3;
       if constexpr (S::W20 == 2) {
         mx = max3n(mx, v[r], v[r + 4]);
-        cnt += f[r] + f[r + 4];
       } else if constexpr (S::TIP2) {
         const float tu = r ? hi(SU) : lo(SU), td = r ? hi(SD) : lo(SD);
         mx = max3n(mx, tu, td);
-        cnt += gtf(tu, A.step_crit) + gtf(td, A.step_crit);  // NaN > crit is false
       }
       pmx[r] = mx;
-      pc[r] = cnt;
+    }
+    if constexpr (S::W20 == 2) {
+      PC = add2(PC, add2(mk(f[0], f[1]), mk(f[4], f[5])));
+    } else if constexpr (S::TIP2) {  // NaN > crit is false
+      PC = add2(PC, add2(mk(gtf(lo(SU), A.step_crit), gtf(hi(SU), A.step_crit)), mk(gtf(lo(SD), A.step_crit), gtf(hi(SD), A.step_crit))));
     }
     L.sh[S0] = V0;
     L.s3mx[S0] = mk(smx[0], smx[1]); L.s3c[S0] = mk(sc[0], sc[1]);
-    L.pcmx[S0] = mk(pmx[0], pmx[1]); L.pcc[S0] = mk(pc[0], pc[1]);
+    L.pcmx[S0] = mk(pmx[0], pmx[1]); L.pcc[S0] = PC;
   }
   // ---- normals / slope / roughness of column jn = ce - 2 (ages: l = 2 - age) -------------------
   const int jn = ce - 2;
@@ -588,7 +606,7 @@ __device__ __forceinline__ void march_step(StepCtx<S>& C, Lane<S>& L, int t, uns
   const int jo = ce - 4;
   if (jo >= C.q1) return;
   {
-    float outv[2];
+    float mx2[2];
     unsigned sflag = 0;
     f2 TL2 = L.sh[S4], TR2 = L.sh[S0];
     if constexpr (S::TIP2) {
@@ -596,36 +614,35 @@ __device__ __forceinline__ void march_step(StepCtx<S>& C, Lane<S>& L, int t, uns
       TL2 = add2(TL2, bc((cm_jo & 4u) ? 0.0f : qn));
       TR2 = add2(TR2, bc((cm_jo & 8u) ? 0.0f : qn));
     }
+    f2 CNT = L.pcc[S2];
+    if constexpr (S::W21 >= 0) CNT = add2(CNT, add2(L.s3c[S1], L.s3c[S3]));
+    if constexpr (S::W22 == 0 || S::TIP2)
+      CNT = add2(CNT, add2(mk(gtf(lo(TL2), A.step_crit), gtf(hi(TL2), A.step_crit)), mk(gtf(lo(TR2), A.step_crit), gtf(hi(TR2), A.step_crit))));
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
       auto R = [&](f2 x) { return r ? hi(x) : lo(x); };
       float mx = R(L.pcmx[S2]);
-      float cnt = R(L.pcc[S2]);
-      if constexpr (S::W21 >= 0) {
-        mx = max3n(mx, R(L.s3mx[S1]), R(L.s3mx[S3]));
-        cnt += R(L.s3c[S1]) + R(L.s3c[S3]);
-      }
-      if constexpr (S::W22 == 0 || S::TIP2) {
-        const float tl = R(TL2), tr = R(TR2);
-        mx = max3n(mx, tl, tr);
-        cnt += gtf(tl, A.step_crit) + gtf(tr, A.step_crit);
-      }
+      if constexpr (S::W21 >= 0) mx = max3n(mx, R(L.s3mx[S1]), R(L.s3mx[S3]));
+      if constexpr (S::W22 == 0 || S::TIP2) mx = max3n(mx, R(TL2), R(TR2));
       sflag |= (mx > 3.0e38f) ? (1u << r) : 0u;  // an infinite elevation reached the window: the slow path sorts it out
-      const float stepMax = fmaxf(mx, 0.0f);
-      const float st = fminf(stepMax, cnt * A.inv_ncrit * stepMax);
-      // st < crit ? 1 - st/crit : 0 ; no finite step_height in the window (mx is NaN) -> layer stays NaN (StepFilter.cpp:169)
-      outv[r] = fmaxf(fmaf(-st, A.inv_step_crit, 1.0f), 0.0f) + (mx - mx);  // mx NaN (or Inf - Inf) keeps the layer NaN
+      mx2[r] = mx;
     }
+    const f2 MX = mk(mx2[0], mx2[1]);
+    const f2 stepMax = mk(fmaxf(mx2[0], 0.0f), fmaxf(mx2[1], 0.0f));
+    const f2 prod = mul2(mul2(CNT, A.k_inv_ncrit), stepMax);
+    const f2 st = mk(fminf(lo(stepMax), lo(prod)), fminf(hi(stepMax), hi(prod)));
+    // st < crit ? 1 - st/crit : 0 ; no finite step_height in the window (mx is NaN) -> layer stays NaN (StepFilter.cpp:169)
+    const f2 lin = fma2(st, A.k_minv_step, A.k_one);
+    const f2 outv = add2(mk(fmaxf(lo(lin), 0.0f), fmaxf(hi(lin), 0.0f)), sub2(MX, MX));  // mx NaN (or Inf - Inf) keeps the layer NaN
     const f2 sl = L.dslope[S2], ro = L.drough[S2];
     const unsigned nf = L.dflag[S2];
+    const f2 tr = mul2(A.k_fuse_w, add2(add2(sl, outv), ro));
     if (C.out_ok) {
       const size_t oc = C.oc;
       *reinterpret_cast<f2*>(A.slope + oc) = sl;
       *reinterpret_cast<f2*>(A.rough + oc) = ro;
-      *reinterpret_cast<float2*>(A.step + oc) = make_float2(outv[0], outv[1]);
-      const float t0 = __fmul_rn(A.fuse_w, __fadd_rn(__fadd_rn(lo(sl), outv[0]), lo(ro)));
-      const float t1 = __fmul_rn(A.fuse_w, __fadd_rn(__fadd_rn(hi(sl), outv[1]), hi(ro)));
-      *reinterpret_cast<float2*>(A.trav + oc) = make_float2(t0, t1);
+      *reinterpret_cast<f2*>(A.step + oc) = outv;
+      *reinterpret_cast<f2*>(A.trav + oc) = tr;
     }
     // certified slow path: append flagged cells (bit 30: normals part, bit 31: step part)
     const unsigned fl = C.out_ok ? (nf | (sflag << 2)) : 0u;  // bits 0/1: normals part of row x/y, bits 2/3: step part
@@ -651,19 +668,26 @@ __global__ void TE_KERNEL_ATTR k_chain_fused(const __grid_constant__ CUtensorMap
 
   const int total_warps = gridDim.x * WARPS_PER_CTA;
   const int gwarp = blockIdx.x * WARPS_PER_CTA + warp;
-  const int units_per_map = A.nstrips * A.nseg;
-  const int nunits = units_per_map * A.nmaps;
+  const int nunits = A.lvl_unit0[NLVL];
   unsigned kglob = 0;  // chunks consumed so far by this warp (stage = kglob % NST, parity = (kglob / NST) & 1)
 
   Lane<S> L;
   StepCtx<S> C{A, ering + lane * 8u, shbuf + lane * 8u, lane, 0, 0, 0, 0ull, 0ull, 0ull, 0ull, false, 0, 0};
 
-  for (int unit = gwarp; unit < nunits; unit += total_warps) {
-    const int mapi = unit / units_per_map, um = unit - mapi * units_per_map;
+  int unit = gwarp;  // the first unit is static, the rest come from the queue
+  while (unit < nunits) {
+    int next = 0;
+    if (lane == 0) next = total_warps + (int)atomicAdd(A.queue, 1u);  // consumed after this unit: the latency hides behind it
+    int u0 = A.lvl_unit0[0], c0 = A.lvl_col0[0], c1 = A.lvl_col0[1], len = A.lvl_len[0], ns = A.lvl_nseg[0];
+    if (unit >= A.lvl_unit0[1]) { u0 = A.lvl_unit0[1]; c0 = A.lvl_col0[1]; c1 = A.lvl_col0[2]; len = A.lvl_len[1]; ns = A.lvl_nseg[1]; }
+    if (unit >= A.lvl_unit0[2]) { u0 = A.lvl_unit0[2]; c0 = A.lvl_col0[2]; c1 = A.lvl_col0[3]; len = A.lvl_len[2]; ns = A.lvl_nseg[2]; }
+    if (unit >= A.lvl_unit0[3]) { u0 = A.lvl_unit0[3]; c0 = A.lvl_col0[3]; c1 = A.lvl_col0[4]; len = A.lvl_len[3]; ns = A.lvl_nseg[3]; }
+    const int u = unit - u0, upm = A.nstrips * ns;
+    const int mapi = u / upm, um = u - mapi * upm;
     const int strip = um % A.nstrips, seg = um / A.nstrips;
     C.s0 = strip * OROWS - 2;
-    C.q0 = A.out_col0 + seg * A.seg_len;
-    C.q1 = min(C.q0 + A.seg_len, A.out_col0 + A.out_ncols);
+    C.q0 = A.out_col0 + c0 + seg * len;
+    C.q1 = min(C.q0 + len, A.out_col0 + c1);
     const int nsteps = (C.q1 - C.q0) + 8;
     const int nchunks = (nsteps + CH - 1) / CH;
     const int row0 = C.s0 + 2 * lane;
@@ -726,6 +750,7 @@ __global__ void TE_KERNEL_ATTR k_chain_fused(const __grid_constant__ CUtensorMap
       cm_cur = cm_next;
     }
     kglob += nchunks;
+    unit = __shfl_sync(FULL, next, 0);
   }
 }
 
@@ -790,6 +815,51 @@ PFN_encodeTiled get_encode() {
   return fn;
 }
 
+// Splits the output columns of every map into up to NLVL runs of segments, longest segments first.  A warp
+// pops (segment, strip) units in that order, so the last units handed out are short and the warps finish
+// within one short unit of each other.  Each unit pays 8 warm-up columns (cheap: the later stages are
+// skipped), so the bulk of the map stays in longer segments; about eight long units per warp measured best
+// from 2048^2 to 8192^2 and for batches of 512^2 maps (profiles/README.md).
+void plan_levels(FusedArgs& a, int out_ncols, int nmaps, int total_warps) {
+  const double share = (double)a.nstrips * out_ncols * nmaps / (double)total_warps;  // strip-columns per warp
+  const int len0 = std::min(128, std::max(16, (int)std::lround(share / 8.0 / 8.0) * 8));
+  int len[NLVL] = {len0, std::max(16, len0 * 3 / 8 / 8 * 8), 16, 16};
+  double frac[NLVL] = {0.80, 0.15, 0.05, 0.0};
+  if (len0 == 16) { frac[0] = 1.0; frac[1] = frac[2] = 0.0; }
+  const char* e = std::getenv("TE_FUSED_SEGS");  // calibration runs only: "len:frac,len:frac,..."
+  if (e && *e) {
+    for (int i = 0; i < NLVL; ++i) { len[i] = 16; frac[i] = 0.0; }
+    int i = 0, l = 0, n = 0;
+    double f = 0.0;
+    while (i < NLVL && std::sscanf(e, "%d:%lf%n", &l, &f, &n) >= 2) {
+      len[i] = std::max(8, l);
+      frac[i] = f;
+      ++i;
+      e += n;
+      if (*e == ',') ++e;
+    }
+  }
+  int col = 0, unit = 0;
+  double cum = 0.0;
+  for (int i = 0; i < NLVL; ++i) {
+    cum += frac[i];
+    int end = (i == NLVL - 1 || cum >= 1.0) ? out_ncols : (int)std::lround(cum * out_ncols);
+    end = std::min(std::max(end, col), out_ncols);
+    bool later = false;
+    for (int j = i + 1; j < NLVL; ++j) later = later || frac[j] > 0.0;
+    if (!later) end = out_ncols;
+    const int ncol = end - col;
+    a.lvl_unit0[i] = unit;
+    a.lvl_col0[i] = col;
+    a.lvl_len[i] = len[i];
+    a.lvl_nseg[i] = (ncol + len[i] - 1) / len[i];
+    unit += a.nstrips * a.lvl_nseg[i] * nmaps;
+    col = end;
+  }
+  a.lvl_unit0[NLVL] = unit;
+  a.lvl_col0[NLVL] = out_ncols;
+}
+
 template <class S, bool KN>
 int launch_shape(FusedState& st, const CUtensorMap& map, const FusedArgs& a, int sms, cudaStream_t s) {
   static bool attr_set = false;
@@ -801,7 +871,7 @@ int launch_shape(FusedState& st, const CUtensorMap& map, const FusedArgs& a, int
     }
     attr_set = true;
   }
-  const int nunits = a.nstrips * a.nseg * a.nmaps;
+  const int nunits = a.lvl_unit0[NLVL];
   int grid = std::min(sms, (nunits + WARPS_PER_CTA - 1) / WARPS_PER_CTA);
   if (grid < 1) grid = 1;
   k_chain_fused<S, KN><<<grid, WARPS_PER_CTA * 32, smem, s>>>(map, a);
@@ -919,17 +989,8 @@ int launch_chain_fused(FusedState& st, const SlabView& v, const ChainDev& p, int
   a.nstrips = (v.rows + OROWS - 1) / OROWS;
   a.nmaps = nmaps;
   a.map_cells = (unsigned)((size_t)v.rows * v.out_ncols);
-  {
-    const int total_warps = sms * WARPS_PER_CTA;
-    const int nseg0 = std::max(1, (v.out_ncols + 199) / 200);
-    const long long units0 = (long long)a.nstrips * nseg0 * nmaps;
-    const long long waves = (units0 + total_warps - 1) / total_warps;
-    long long nseg = std::max<long long>(1, waves * total_warps / ((long long)a.nstrips * nmaps));
-    int seg_len = (int)((v.out_ncols + nseg - 1) / nseg);
-    if (seg_len < 16) seg_len = std::min(16, v.out_ncols);
-    a.seg_len = seg_len;
-    a.nseg = (v.out_ncols + seg_len - 1) / seg_len;
-  }
+  plan_levels(a, v.out_ncols, nmaps, sms * WARPS_PER_CTA);
+  a.queue = count + 32;  // its own 128-byte line of the counter block
   const double N = wn.n, K2 = wn.k2;
   a.a_cov = (float)(res * res * K2 / N);
   a.half_a = 0.5f * a.a_cov;
@@ -956,6 +1017,7 @@ int launch_chain_fused(FusedState& st, const SlabView& v, const ChainDev& p, int
   a.k_invN = B2(1.0 / N); a.k_minvN = B2(-1.0 / N); a.k_kp = B2(-res / N); a.k_half_a = B2(0.5 * (double)a.a_cov);
   a.k_nnm1 = B2(N / (N - 1.0)); a.k_rough_thr = B2((double)a.rough_thr);
   a.k_minv_slope = B2(-1.0 / p.slope_crit); a.k_minv_rough = B2(-1.0 / p.rough_crit);
+  a.k_inv_ncrit = B2((double)a.inv_ncrit); a.k_minv_step = B2(-(double)a.inv_step_crit); a.k_fuse_w = B2((double)a.fuse_w);
   a.k_m0 = B2(wn.w[2] >= 0 ? 2 * wn.w[2] + 1 : 0); a.k_m1 = B2(wn.w[1] >= 0 ? 2 * wn.w[1] + 1 : 0);
   a.k_1em5 = B2(1e-5); a.k_1em10a = B2(1e-10 * (double)a.a_cov); a.k_mcond = B2(-cond_k);
   a.k_2p24 = B2(16777216.0); a.k_7p1em6 = B2(7.1e-6); a.k_2em6 = B2(2e-6); a.k_1em3 = B2(1e-3);
