@@ -104,30 +104,52 @@ __device__ bool normals_t2(const FixupArgs& A, const Elev& E, int i, int j, floa
       }
     }
   }
-  double n = 0, su = 0, sv = 0, sw = 0, suu = 0, suv = 0, svv = 0, suw = 0, svw = 0, sww = 0;
+  // The moments of the cell offsets depend only on WHICH cells are valid: integer sums over the 25-bit validity mask
+  // (bit (l+2)*5 + (k+2)), exact, instead of 25 x 6 fp64 accumulations.  Only the four moments that involve z are summed.
+  unsigned mask = 0;
+#pragma unroll
+  for (int l = -2; l <= 2; ++l)
+#pragma unroll
+    for (int k = -2; k <= 2; ++k) mask |= finitef(zw[l + 2][k + 2]) ? (1u << ((l + 2) * 5 + (k + 2))) : 0u;
+  constexpr unsigned KM = 0x108421u, LM = 0x1fu;  // cells of row offset k = -2 / of column offset l = -2
+  const int k_m2 = __popc(mask & KM), k_m1 = __popc(mask & (KM << 1)), k_p1 = __popc(mask & (KM << 3)), k_p2 = __popc(mask & (KM << 4));
+  const int l_m2 = __popc(mask & LM), l_m1 = __popc(mask & (LM << 5)), l_p1 = __popc(mask & (LM << 15)), l_p2 = __popc(mask & (LM << 20));
+  auto bit = [](int k, int l) { return 1u << ((l + 2) * 5 + (k + 2)); };
+  const unsigned kl_p1 = bit(1, 1) | bit(-1, -1), kl_m1 = bit(1, -1) | bit(-1, 1);
+  const unsigned kl_p2 = bit(2, 1) | bit(1, 2) | bit(-2, -1) | bit(-1, -2), kl_m2 = bit(2, -1) | bit(-1, 2) | bit(-2, 1) | bit(1, -2);
+  const unsigned kl_p4 = bit(2, 2) | bit(-2, -2), kl_m4 = bit(2, -2) | bit(-2, 2);
+  const int ik = 2 * (k_p2 - k_m2) + (k_p1 - k_m1), il = 2 * (l_p2 - l_m2) + (l_p1 - l_m1);
+  const int ikk = 4 * (k_p2 + k_m2) + (k_p1 + k_m1), ill = 4 * (l_p2 + l_m2) + (l_p1 + l_m1);
+  const int ikl = (__popc(mask & kl_p1) - __popc(mask & kl_m1)) + 2 * (__popc(mask & kl_p2) - __popc(mask & kl_m2)) +
+                  4 * (__popc(mask & kl_p4) - __popc(mask & kl_m4));
+  const double res2 = A.res * A.res;
+  const double n = (double)__popc(mask);
+  const double su = -A.res * (double)ik, sv = -A.res * (double)il;  // u = -res*k, v = -res*l
+  const double suu = res2 * (double)ikk, svv = res2 * (double)ill, suv = res2 * (double)ikl;
+  double sw = 0, suw = 0, svw = 0, sww = 0;
 #pragma unroll
   for (int l = -2; l <= 2; ++l)
 #pragma unroll
     for (int k = -2; k <= 2; ++k) {
       const float z = zw[l + 2][k + 2];
-      const bool ok = finitef(z);
-      const double m = ok ? 1.0 : 0.0;                       // invalid cells contribute exact zeros
-      const double u = m * (-A.res * (double)k), v = m * (-A.res * (double)l), d = ok ? (double)z - (double)zc : 0.0;
-      n += m; su += u; sv += v; sw += d;
-      suu += u * u; suv += u * v; svv += v * v; suw += u * d; svw += v * d; sww += d * d;
+      const double d = finitef(z) ? (double)z - (double)zc : 0.0;  // invalid cells contribute exact zeros
+      sw += d;
+      if (k != 0) suw = fma(-A.res * (double)k, d, suw);
+      if (l != 0) svw = fma(-A.res * (double)l, d, svw);
+      sww = fma(d, d, sww);
     }
   double nx = 0.0, ny = 0.0, nz = 1.0;
   const double mu = su / n, mv = sv / n, mw = sw / n;
   // scatter matrix sum (p - mean)(p - mean)^T
-  const double xx = suu - su * mu, xy = suv - su * mv, xz = suw - su * mw;
-  const double yy = svv - sv * mv, yz = svw - sv * mw, zz = sww - sw * mw;
+  const double xx = fma(-su, mu, suu), xy = fma(-su, mv, suv), xz = fma(-su, mw, suw);
+  const double yy = fma(-sv, mv, svv), yz = fma(-sv, mw, svw), zz = fma(-sw, mw, sww);
   if (n >= 3.0 && zz > 0.0) {
     double bx, by, bz;
     if (n == A.n_full) {
       // full disk window: scatter = [[a,0,p],[0,a,q],[p,q,c]] (sums of u, v, uv vanish by symmetry) and
       // the eigen-problem collapses to 2x2 — robust even when two eigenvalues nearly coincide
-      const double a = 0.5 * (xx + yy), g2 = xz * xz + yz * yz;
-      const double h = 0.5 * (a - zz), D = sqrt(h * h + g2);
+      const double a = 0.5 * (xx + yy), g2 = fma(xz, xz, yz * yz);
+      const double h = 0.5 * (a - zz), D = sqrt(fma(h, h, g2));
       const double dph = D + fabs(h);
       if (!(dph > 0.0)) return false;
       const double qq = g2 / dph;
@@ -145,14 +167,14 @@ __device__ bool normals_t2(const FixupArgs& A, const Elev& E, int i, int j, floa
       bool conv = false;
 #pragma unroll 1
       for (int it = 0; it < 40; ++it) {  // Newton from below: monotone convergence to the smallest root
-        const double p = ((-lam + c2) * lam - c1) * lam + c0;
-        dp = (-3.0 * lam + 2.0 * c2) * lam - c1;
+        const double p = fma(fma(c2 - lam, lam, -c1), lam, c0);
+        dp = fma(fma(-3.0, lam, 2.0 * c2), lam, -c1);
         if (dp == 0.0) break;
         const double step = p / dp;
         lam -= step;
         if (fabs(step) <= 1e-15 * c2) { conv = true; break; }
       }
-      dp = (-3.0 * lam + 2.0 * c2) * lam - c1;
+      dp = fma(fma(-3.0, lam, 2.0 * c2), lam, -c1);
       // rank: lambda0 at the reference's rank-threshold scale -> the literal QR decides (tier 3);
       // conditioning: |p'(lambda0)| = (l1 - l0)(l2 - l0) must leave the cross products accurate
       if (!conv || !(lam > 1e-9 * c2) || !(fabs(dp) > 1e-4 * c2 * c2)) return false;
@@ -167,7 +189,7 @@ __device__ bool normals_t2(const FixupArgs& A, const Elev& E, int i, int j, floa
       if (q1 > bq) { bx = v1x; by = v1y; bz = v1z; bq = q1; }
       if (q2 > bq) { bx = v2x; by = v2y; bz = v2z; bq = q2; }
     }
-    const double bq = bx * bx + by * by + bz * bz;
+    const double bq = fma(bx, bx, fma(by, by, bz * bz));
     if (!(bq > 0.0)) return false;
     const double inv = 1.0 / sqrt(bq);
     nx = bx * inv; ny = by * inv; nz = bz * inv;
@@ -190,19 +212,10 @@ __device__ bool normals_t2(const FixupArgs& A, const Elev& E, int i, int j, floa
   slope = (float)(th < A.slope_crit ? 1.0 - th / A.slope_crit : 0.0);
   // roughness with the float32 normal (RoughnessFilter.cpp:108-117)
   const double NX = fnx, NY = fny, NZ = fnz;
-  double sum = 0.0;
-  const double cnt = n;
-  const double plane = mu * NX + mv * NY + mw * NZ;
-#pragma unroll
-  for (int l = -2; l <= 2; ++l)
-#pragma unroll
-    for (int k = -2; k <= 2; ++k) {
-      const float z = zw[l + 2][k + 2];
-      const bool ok = finitef(z);
-      const double d = NX * (-A.res * (double)k) + NY * (-A.res * (double)l) + NZ * ((double)z - (double)zc) - plane;
-      sum += ok ? d * d : 0.0;
-    }
-  const double r = sqrt(sum / (cnt - 1.0));  // one point: 0/0 = NaN -> comparison false -> 0.0
+  // sum over the window of (N . (p - mean))^2 = N^T S N with the scatter matrix S already at hand (RoughnessFilter.cpp
+  // sums it point by point; the quadratic form loses at most ~1e-16 * |S| absolutely, ~1e-12 of the layer value)
+  const double sum = fmax(NX * (NX * xx + 2.0 * (NY * xy + NZ * xz)) + NY * (NY * yy + 2.0 * NZ * yz) + NZ * NZ * zz, 0.0);
+  const double r = sqrt(sum / (n - 1.0));  // one point: 0/0 = NaN -> comparison false -> 0.0
   rough = (float)(r < A.rough_crit ? 1.0 - r / A.rough_crit : 0.0);
   return true;
 }

@@ -379,7 +379,13 @@ __global__ void __launch_bounds__(128) k_fixup_cells(SlabView v, ChainDev p, con
                                                      const unsigned int* __restrict__ count, unsigned int cap) {
   unsigned int n = *count;
   if (n > cap) n = cap;
-  for (unsigned int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+  // A literal cell is ~50 us of serial, branchy double-precision code.  The usual handful of cells gets one warp each
+  // (lane 0 works): no divergence between cells with different sweep counts, and the cells run on different SMs.
+  // Long lists (degenerate maps, e.g. exact planes everywhere) fall back to one cell per thread.
+  const unsigned int nthreads = gridDim.x * blockDim.x, tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool sparse = n <= (nthreads >> 5);
+  if (sparse && (threadIdx.x & 31u) != 0u) return;
+  for (unsigned int k = sparse ? (tid >> 5) : tid; k < n; k += sparse ? (nthreads >> 5) : nthreads) {
     const unsigned int w = list[k];
     const unsigned int c = w & 0x3fffffffu;  // bit 30: normals part, bit 31: step part
     const unsigned int map_cells = (unsigned)v.rows * (unsigned)v.out_ncols;
