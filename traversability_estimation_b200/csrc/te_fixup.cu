@@ -84,33 +84,52 @@ __device__ bool normals_t2(const FixupArgs& A, const Elev& E, int i, int j, floa
     fnx = fny = fnz = slope = rough = nanf_();
     return true;
   }
-  // gather the 5 x 5 neighbourhood with 25 unconditional, independent loads (indices clamped into the buffer; what lies
-  // outside the map / window / buffer is masked to NaN afterwards), then work from registers without branches
+  // gather the 5 x 5 neighbourhood with 25 unconditional, independent loads, then work from registers without branches.
+  // A cell that is outside the map / window / buffer or not finite is replaced by the centre value (so its deviation below
+  // is an exact zero) and stays out of the validity mask (bit (l+2)*5 + (k+2)).
   float zw[5][5];
+  unsigned mask = 0;
   {
     const int lb0 = j - A.in_col0;
+    unsigned shape = 0;  // cells of the disk window
 #pragma unroll
     for (int l = -2; l <= 2; ++l) {
-      const int b = j + l, lb = lb0 + l;
-      const bool col_ok = b >= 0 && b < A.cols_total && lb >= 0 && lb < A.in_ncols;
-      const float* col = E.e + (size_t)min(max(lb, 0), A.in_ncols - 1) * A.rows;
       const int w = A.wn[l < 0 ? -l : l];
 #pragma unroll
-      for (int k = -2; k <= 2; ++k) {
-        const int a = i + k;
-        const float v = __ldg(col + min(max(a, 0), A.rows - 1));
-        const bool ok = col_ok && a >= 0 && a < A.rows && k >= -w && k <= w && finitef(v);
-        zw[l + 2][k + 2] = ok ? v : nanf_();
+      for (int k = -2; k <= 2; ++k) shape |= (k >= -w && k <= w) ? (1u << ((l + 2) * 5 + (k + 2))) : 0u;
+    }
+    if (i >= 2 && i + 2 < A.rows && j >= 2 && j + 2 < A.cols_total && lb0 >= 2 && lb0 + 2 < A.in_ncols) {
+      const float* base = E.e + (size_t)lb0 * A.rows + i;  // interior cell: no clamping
+#pragma unroll
+      for (int l = -2; l <= 2; ++l)
+#pragma unroll
+        for (int k = -2; k <= 2; ++k) {
+          const float v = __ldg(base + (ptrdiff_t)l * A.rows + k);
+          const unsigned bitm = 1u << ((l + 2) * 5 + (k + 2));
+          const bool ok = (shape & bitm) != 0u && finitef(v);
+          zw[l + 2][k + 2] = ok ? v : zc;
+          mask |= ok ? bitm : 0u;
+        }
+    } else {
+#pragma unroll
+      for (int l = -2; l <= 2; ++l) {
+        const int b = j + l, lb = lb0 + l;
+        const bool col_ok = b >= 0 && b < A.cols_total && lb >= 0 && lb < A.in_ncols;
+        const float* col = E.e + (size_t)min(max(lb, 0), A.in_ncols - 1) * A.rows;
+#pragma unroll
+        for (int k = -2; k <= 2; ++k) {
+          const int a = i + k;
+          const float v = __ldg(col + min(max(a, 0), A.rows - 1));
+          const unsigned bitm = 1u << ((l + 2) * 5 + (k + 2));
+          const bool ok = col_ok && a >= 0 && a < A.rows && (shape & bitm) != 0u && finitef(v);
+          zw[l + 2][k + 2] = ok ? v : zc;
+          mask |= ok ? bitm : 0u;
+        }
       }
     }
   }
-  // The moments of the cell offsets depend only on WHICH cells are valid: integer sums over the 25-bit validity mask
-  // (bit (l+2)*5 + (k+2)), exact, instead of 25 x 6 fp64 accumulations.  Only the four moments that involve z are summed.
-  unsigned mask = 0;
-#pragma unroll
-  for (int l = -2; l <= 2; ++l)
-#pragma unroll
-    for (int k = -2; k <= 2; ++k) mask |= finitef(zw[l + 2][k + 2]) ? (1u << ((l + 2) * 5 + (k + 2))) : 0u;
+  // The moments of the cell offsets depend only on WHICH cells are valid: integer sums over the 25-bit validity mask,
+  // exact, instead of 25 x 6 fp64 accumulations.  Only the four moments that involve z are summed.
   constexpr unsigned KM = 0x108421u, LM = 0x1fu;  // cells of row offset k = -2 / of column offset l = -2
   const int k_m2 = __popc(mask & KM), k_m1 = __popc(mask & (KM << 1)), k_p1 = __popc(mask & (KM << 3)), k_p2 = __popc(mask & (KM << 4));
   const int l_m2 = __popc(mask & LM), l_m1 = __popc(mask & (LM << 5)), l_p1 = __popc(mask & (LM << 15)), l_p2 = __popc(mask & (LM << 20));
@@ -131,15 +150,15 @@ __device__ bool normals_t2(const FixupArgs& A, const Elev& E, int i, int j, floa
   for (int l = -2; l <= 2; ++l)
 #pragma unroll
     for (int k = -2; k <= 2; ++k) {
-      const float z = zw[l + 2][k + 2];
-      const double d = finitef(z) ? (double)z - (double)zc : 0.0;  // invalid cells contribute exact zeros
+      const double d = (double)zw[l + 2][k + 2] - (double)zc;  // invalid cells: exact zero
       sw += d;
       if (k != 0) suw = fma(-A.res * (double)k, d, suw);
       if (l != 0) svw = fma(-A.res * (double)l, d, svw);
       sww = fma(d, d, sww);
     }
   double nx = 0.0, ny = 0.0, nz = 1.0;
-  const double mu = su / n, mv = sv / n, mw = sw / n;
+  const double rn = 1.0 / n;
+  const double mu = su * rn, mv = sv * rn, mw = sw * rn;
   // scatter matrix sum (p - mean)(p - mean)^T
   const double xx = fma(-su, mu, suu), xy = fma(-su, mv, suv), xz = fma(-su, mw, suw);
   const double yy = fma(-sv, mv, svv), yz = fma(-sv, mw, svw), zz = fma(-sw, mw, sww);
