@@ -379,7 +379,7 @@ __global__ void __launch_bounds__(128) k_fixup_cells(SlabView v, ChainDev p, con
                                                      const unsigned int* __restrict__ count, unsigned int cap) {
   unsigned int n = *count;
   if (n > cap) n = cap;
-  // A literal cell is ~50 us of serial, branchy double-precision code.  The usual handful of cells gets one warp each
+  // A literal cell is ~40 us of serial, branchy double-precision code (half of it instruction fetch).  The usual handful of cells gets one warp each
   // (lane 0 works): no divergence between cells with different sweep counts, and the cells run on different SMs.
   // Long lists (degenerate maps, e.g. exact planes everywhere) fall back to one cell per thread.
   const unsigned int nthreads = gridDim.x * blockDim.x, tid = blockIdx.x * blockDim.x + threadIdx.x;
