@@ -116,9 +116,14 @@ int te_get_stats(te_ctx* ctx, int64_t* kernel_launches, int64_t* slow_path_cells
 int te_enable_timing(te_ctx* ctx, int on);
 int te_get_timing(te_ctx* ctx, double* main_ms, double* fixup_ms, int64_t* samples);
 /* Work-list counters of the last fused launch: [0] cells the fp32 stencil could not certify (tier 2,
- * fp64 on centred coordinates); [4] cells tier 2 passed on to the literal kernel (tier 3); [1..3] only
- * when TE_FUSED_STATS is set: cells flagged for eigenvalue cancellation, conditioning, n_z rounding. */
+ * fp64 on centred coordinates); [4] cells tier 2 passed on to the literal kernel (tier 3); [1..3] reserved (0). */
 int te_get_flag_counters(te_ctx* ctx, uint32_t out[5]);
+/* Work decomposition the fused kernel uses for `nmaps` maps of rows x out_ncols output cells on a GPU with `sms`
+ * multiprocessors (host arithmetic only, needs no GPU; no reference counterpart — the reference iterates cell by cell).
+ * Units are (level, map, column segment, 60-row strip), popped from a queue in that order; a level is a run of columns cut
+ * into segments of one length.  out[0] = strips per map, out[1] = levels, then per level {first unit, first column,
+ * segment length, segments per map}, then the total number of units: 2 + 4*levels + 1 values (levels <= 4, so 19). */
+int te_fused_plan(int rows, int out_ncols, int nmaps, int sms, int32_t out[19]);
 
 /* filters::SlopeFilter<grid_map::GridMap>::update — traversability_estimation_filters/src/SlopeFilter.cpp:59-89.
  * in: surface_normal_z, out: the `map_type` layer. */

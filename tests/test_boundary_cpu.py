@@ -27,6 +27,42 @@ def test_library_exports_every_declared_symbol(te):
     assert set(te.capi.EXPORTS) <= set(_declared())
 
 
+@pytest.mark.parametrize("rows,cols,nmaps,sms", [(8192, 8192, 1, 148), (2048, 2048, 1, 148), (4096, 4096, 1, 148), (512, 512, 256, 148),
+                                                  (192, 160, 1, 148), (60, 7, 1, 148), (8192, 2052, 1, 148), (1000, 333, 3, 132)])
+def test_fused_work_units_tile_every_map_exactly_once(te, rows, cols, nmaps, sms):
+    """The fused kernel's queue of (level, map, segment, strip) units — decoded here the way the kernel decodes a unit id —
+    covers every (map, strip, column) once, hands out longer segments first and ends on the unit count it reports."""
+    import numpy as np
+    plan = te.capi.fused_plan(rows, cols, nmaps, sms)
+    strips, levels = plan["strips"], plan["levels"]
+    assert strips == (rows + 59) // 60
+    cover = np.zeros((nmaps, strips, cols), dtype=np.int32)
+    unit = 0
+    col_ends = [lv["col0"] for lv in levels[1:]] + [cols]
+    lens = []
+    for lv, c1 in zip(levels, col_ends):
+        assert lv["unit0"] == unit
+        upm = strips * lv["nseg"]
+        for u in range(upm * nmaps):
+            mapi, um = divmod(u, upm)
+            seg, strip = divmod(um, strips)
+            q0 = lv["col0"] + seg * lv["seg_len"]
+            q1 = min(q0 + lv["seg_len"], c1)
+            assert q0 < q1 <= cols
+            cover[mapi, strip, q0:q1] += 1
+        unit += upm * nmaps
+        if lv["nseg"]:
+            lens.append(lv["seg_len"])
+    assert unit == plan["units"]
+    assert (cover == 1).all()
+    assert lens == sorted(lens, reverse=True) and min(lens) >= 8
+
+
+def test_fused_plan_rejects_bad_sizes(te):
+    with pytest.raises(te.TEError):
+        te.capi.fused_plan(0, 16)
+
+
 def test_no_cpu_fallback(te):
     import torch
     if torch.cuda.is_available():

@@ -14,7 +14,7 @@ MEM_HOST, MEM_DEVICE = 0, 1
 KERNEL_AUTO, KERNEL_GENERIC, KERNEL_FUSED = 0, 1, 2
 
 EXPORTS = ["te_create", "te_destroy", "te_last_error", "te_abi_version", "te_set_stream", "te_synchronize",
-           "te_set_kernel", "te_get_stats", "te_enable_timing", "te_get_timing", "te_get_flag_counters", "te_slope", "te_normals", "te_step", "te_roughness", "te_chain",
+           "te_set_kernel", "te_get_stats", "te_enable_timing", "te_get_timing", "te_get_flag_counters", "te_fused_plan", "te_slope", "te_normals", "te_step", "te_roughness", "te_chain",
            "te_chain_batched", "te_footprint", "te_ipc_export", "te_ipc_open", "te_ipc_close"]
 
 
@@ -113,6 +113,19 @@ def load_library():
         L.te_ipc_close.argtypes = [vp]
         _lib = L
     return _lib
+
+
+def fused_plan(rows: int, out_ncols: int, nmaps: int = 1, sms: int = 148) -> dict:
+    """te_fused_plan: the (level, map, segment, strip) work units of the fused launch; host arithmetic, no GPU needed."""
+    L = load_library()
+    out = (C.c_int32 * 19)()
+    L.te_fused_plan.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int32)]
+    rc = L.te_fused_plan(rows, out_ncols, nmaps, sms, out)
+    if rc != 0:
+        raise TEError(rc, "te_fused_plan: invalid argument")
+    nl = out[1]
+    levels = [dict(unit0=out[2 + 4 * i], col0=out[3 + 4 * i], seg_len=out[4 + 4 * i], nseg=out[5 + 4 * i]) for i in range(nl)]
+    return {"strips": out[0], "levels": levels, "units": out[2 + 4 * nl]}
 
 
 def _addr(a):

@@ -411,6 +411,14 @@ int te_get_timing(te_ctx* c, double* main_ms, double* fixup_ms, int64_t* samples
   return TE_OK;
 }
 
+int te_fused_plan(int rows, int out_ncols, int nmaps, int sms, int32_t out[19]) {
+  if (rows <= 0 || out_ncols <= 0 || nmaps <= 0 || sms <= 0 || !out) return TE_ERR_BAD_ARG;
+  int tmp[19];
+  te::fused_plan(rows, out_ncols, nmaps, sms, tmp);
+  for (int i = 0; i < 19; ++i) out[i] = tmp[i];
+  return TE_OK;
+}
+
 int te_get_flag_counters(te_ctx* c, uint32_t out[5]) {
   TE_ENTER(c);
   if (!out) return fail(TE_ERR_BAD_ARG, "null argument");

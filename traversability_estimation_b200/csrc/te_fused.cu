@@ -880,6 +880,21 @@ int launch_shape(FusedState& st, const CUtensorMap& map, const FusedArgs& a, int
 
 }  // namespace
 
+void fused_plan(int rows, int out_ncols, int nmaps, int sms, int out[19]) {
+  FusedArgs a{};
+  a.nstrips = (rows + OROWS - 1) / OROWS;
+  plan_levels(a, out_ncols, nmaps, sms * WARPS_PER_CTA);
+  out[0] = a.nstrips;
+  out[1] = NLVL;
+  for (int i = 0; i < NLVL; ++i) {
+    out[2 + 4 * i] = a.lvl_unit0[i];
+    out[3 + 4 * i] = a.lvl_col0[i];
+    out[4 + 4 * i] = a.lvl_len[i];
+    out[5 + 4 * i] = a.lvl_nseg[i];
+  }
+  out[2 + 4 * NLVL] = a.lvl_unit0[NLVL];
+}
+
 void FusedState::release() {
   if (d_rowmask) cudaFree(d_rowmask);
   if (d_colmask) cudaFree(d_colmask);

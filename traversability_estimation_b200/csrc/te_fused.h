@@ -46,6 +46,9 @@ void launch_fixup_t2(const FixupArgs& a, const float* elev, const ChainOut& o, c
                      unsigned cap, unsigned* list3, unsigned* count3, int sms, cudaStream_t s);
 
 // Returns 0 on success.  Cells whose result could not be certified in fp32 are appended to `list`.
+// Work decomposition of the fused launch (see te_fused_plan in include/te_b200.h); host arithmetic only.
+void fused_plan(int rows, int out_ncols, int nmaps, int sms, int out[19]);
+
 int launch_chain_fused(FusedState& st, const SlabView& v, const ChainDev& p, int nmaps, const float* elev, const ChainOut& o,
                        unsigned* list, unsigned* count, unsigned cap, int sms, cudaStream_t s);
 
