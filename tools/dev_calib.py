@@ -1,11 +1,10 @@
-"""Calibration run: flagged-cell causes and fp32 error vs certification constants (dev tool, GPU)."""
+"""Calibration run: flagged-cell count and fp32 error against the oracle for a sweep of the certification constants (dev tool, GPU)."""
 import os, sys, json
 sys.path.insert(0, '/root/repo'); sys.path.insert(0, '/root/repo/tools'); sys.path.insert(0, '/root/repo/tests')
 import numpy as np, synth, torch, bench
 import traversability_estimation_b200 as te
 from oracle import binding as ob
 from helpers import compare_layer
-os.environ['TE_FUSED_STATS'] = '1'
 rows = cols = 1024
 dev = torch.device('cuda', 0)
 z_t = bench.terrain_torch(torch, rows, 0, cols, cols, 3, 0.0, dev)
