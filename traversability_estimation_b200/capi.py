@@ -8,7 +8,9 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB = os.path.join(_HERE, "libte_b200.so")
+# TE_B200_LIBRARY: development only — load a variant built with `make -C csrc variant NAME=... EXTRA=...` (several builds
+# of the kernels can then be timed in one GPU session); the product library is the one next to this file.
+_LIB = os.environ.get("TE_B200_LIBRARY") or os.path.join(_HERE, "libte_b200.so")
 
 MEM_HOST, MEM_DEVICE = 0, 1
 KERNEL_AUTO, KERNEL_GENERIC, KERNEL_FUSED = 0, 1, 2

@@ -44,7 +44,7 @@ constexpr int STAGE_BYTES = 1408;  // EROWS*CH*4 = 1360, padded so every stage i
 constexpr int SHBUF_BYTES = 288;   // 2 pad + 64 + 2 pad floats, padded
 constexpr int WARP_SMEM_BYTES = NST * STAGE_BYTES + 2 * SHBUF_BYTES + 64;  // 6272 = 49 * 128
 #ifndef TE_WPC
-#define TE_WPC 12
+#define TE_WPC 8
 #endif
 constexpr int WARPS_PER_CTA = TE_WPC;
 #ifdef TE_REGS
