@@ -8,9 +8,10 @@
 // Execution model (DESIGN.md §"fused stencil"):
 //   * The layer is column-major, row index contiguous.  A WARP owns a strip of 64 rows (two adjacent
 //     rows per lane, so all arithmetic is issued as packed f32x2 FFMA2/FADD2) and marches along the
-//     column index.  Warps are autonomous: each has its own TMA ring (4 stages x 5 columns x 72 rows,
+//     column index.  Warps are autonomous: each has its own TMA ring (4 stages x 5 columns x 68 rows,
 //     NaN out-of-bounds fill so map borders look like invalid cells), its own mbarriers and a tiny
-//     step_height exchange buffer; there is no __syncthreads in the kernel.
+//     step_height exchange buffer; there is no __syncthreads in the kernel.  Work units are (60-row strip,
+//     column segment) pairs popped from a device queue, long segments first (plan_levels).
 //   * Everything a lane needs from columns other than the arriving one lives in registers as
 //     five-deep rings indexed at compile time (the march is unrolled by 5 = ring depth = TMA chunk).
 //   * Surface normals use the closed form of the 3x3 eigen-problem that holds for a full disk window
@@ -21,7 +22,8 @@
 //     poisoning of the moments / of the NaN-propagating min-max), whose n_z lies too close to a
 //     float32 rounding boundary where acos amplifies it, whose scatter matrix is numerically
 //     rank-deficient, or whose roughness cancels too far, is appended to a work list and recomputed
-//     by the literal double-precision kernel (te_generic.cu: k_fixup_cells).
+//     in fp64 on centred coordinates (te_fixup.cu: k_fixup_t2), which hands what it cannot decide
+//     either to the literal double-precision kernel (te_generic.cu: k_fixup_cells).
 #include <cuda.h>
 #include <cuda_runtime.h>
 
