@@ -44,9 +44,19 @@ constexpr int CH = 5;              // columns per TMA chunk = unroll factor = ri
 constexpr int NST = 4;             // TMA ring stages per warp
 constexpr int STAGE_BYTES = 1408;  // EROWS*CH*4 = 1360, padded so every stage is 128-byte aligned
 constexpr int SHBUF_BYTES = 288;   // 2 pad + 64 + 2 pad floats, padded
-constexpr int WARP_SMEM_BYTES = NST * STAGE_BYTES + 2 * SHBUF_BYTES + 64;  // 6272 = 49 * 128
+// TE_SMEM_RINGS=1 (default): the run-sum and column-statistics rings live in shared memory instead of registers (one
+// 8-byte element per lane and slot: conflict-free), which brings the kernel to 154 registers — under the 168 that a third
+// warp per scheduler needs (the register file is four 16 K partitions) — so 12 warps fit per SM (TE_WPC=12 TE_REGS=168).
+// TE_SMEM_RINGS=0 TE_WPC=8 is the all-register build (247 registers, 8 warps per SM).
+#ifndef TE_SMEM_RINGS
+#define TE_SMEM_RINGS 1
+#endif
+constexpr bool SMEM_RINGS = TE_SMEM_RINGS != 0;
+enum RingId { R_A1, R_B1, R_Q1, R_A2, R_B2, R_Q2, R_C1MN, R_C1MX, R_S3MX, R_S3C, NRING };
+constexpr int RING_BYTES = SMEM_RINGS ? NRING * 5 * 32 * 8 : 0;
+constexpr int WARP_SMEM_BYTES = NST * STAGE_BYTES + 2 * SHBUF_BYTES + 64 + RING_BYTES;  // 6272 = 49 * 128 (+ 12800 = 100 * 128)
 #ifndef TE_WPC
-#define TE_WPC 8
+#define TE_WPC 12
 #endif
 constexpr int WARPS_PER_CTA = TE_WPC;
 #ifdef TE_REGS
@@ -272,22 +282,34 @@ struct Lane {
   unsigned dflag[5];                 // certification flags of the normals stage (bit0 row x, bit1 row y)
 };
 
-template <int W, class S>
-__device__ __forceinline__ f2 runA(const Lane<S>& L, int s) {
-  if constexpr (W == 2) return L.a2[s];
-  else if constexpr (W == 1) return L.a1[s];
+// Ring access.  A value is always written to its register slot; with SMEM_RINGS it is also stored to shared memory and
+// every read of a slot other than the one written in this very step comes from there, so the register copy dies with the step.
+template <int RID, int SLOT, class CT>
+__device__ __forceinline__ void ring_put(const CT& C, f2 (&reg)[5], f2 v) {
+  reg[SLOT] = v;
+  if constexpr (SMEM_RINGS) C.rg[(RID * 5 + SLOT) * 32] = v;
+}
+template <int RID, int SLOT, int S0, class CT>
+__device__ __forceinline__ f2 ring_get(const CT& C, const f2 (&reg)[5]) {
+  if constexpr (SMEM_RINGS && SLOT != S0) return C.rg[(RID * 5 + SLOT) * 32];
+  else return reg[SLOT];
+}
+template <int W, int SLOT, int S0, class CT, class S>
+__device__ __forceinline__ f2 runA(const CT& C, const Lane<S>& L) {
+  if constexpr (W == 2) return ring_get<R_A2, SLOT, S0>(C, L.a2);
+  else if constexpr (W == 1) return ring_get<R_A1, SLOT, S0>(C, L.a1);
   else return 0ull;
 }
-template <int W, class S>
-__device__ __forceinline__ f2 runB(const Lane<S>& L, int s) {
-  if constexpr (W == 2) return L.b2[s];
-  else if constexpr (W == 1) return L.b1[s];
+template <int W, int SLOT, int S0, class CT, class S>
+__device__ __forceinline__ f2 runB(const CT& C, const Lane<S>& L) {
+  if constexpr (W == 2) return ring_get<R_B2, SLOT, S0>(C, L.b2);
+  else if constexpr (W == 1) return ring_get<R_B1, SLOT, S0>(C, L.b1);
   else return 0ull;
 }
-template <int W, class S>
-__device__ __forceinline__ f2 runQ(const Lane<S>& L, int s) {
-  if constexpr (W == 2) return L.q2[s];
-  else if constexpr (W == 1) return L.q1[s];
+template <int W, int SLOT, int S0, class CT, class S>
+__device__ __forceinline__ f2 runQ(const CT& C, const Lane<S>& L) {
+  if constexpr (W == 2) return ring_get<R_Q2, SLOT, S0>(C, L.q2);
+  else if constexpr (W == 1) return ring_get<R_Q1, SLOT, S0>(C, L.q1);
   else return 0ull;
 }
 
@@ -437,6 +459,7 @@ struct StepCtx {
   int q0, q1;         // output columns of the unit
   f2 tipU1, tipD1;    // pass-1 row tips: +0.0 where the on-circle offset (-2,0)/(+2,0) belongs to the window, NaN where not
   f2 tipU2, tipD2;    // same for pass 2
+  f2* rg;             // SMEM_RINGS: the lane's element of ring 0 / slot 0 in shared memory (rings are 32 lanes x 8 bytes apart)
   bool out_ok;        // lane produces output rows (lanes 1..30 and inside the map)
   size_t oc;          // running output offset (column jo, lane's first row)
   size_t ocn;         // same for the normals stage (column jn)
@@ -463,12 +486,12 @@ __device__ __forceinline__ void march_step(StepCtx<S>& C, Lane<S>& L, int t, uns
     const f2 A1 = add2(D1, Dm1);
     const f2 B1 = sub2(ZP1, ZM1);
     const f2 Q1 = fma2(D1, D1, mul2(Dm1, Dm1));
-    if constexpr (S::NEED_N1) { L.a1[S0] = A1; L.b1[S0] = B1; L.q1[S0] = Q1; }
+    if constexpr (S::NEED_N1) { ring_put<R_A1, S0>(C, L.a1, A1); ring_put<R_B1, S0>(C, L.b1, B1); ring_put<R_Q1, S0>(C, L.q1, Q1); }
     if constexpr (S::NEED_N2) {
       const f2 D2 = sub2(ZP2, Z0), Dm2 = sub2(ZM2, Z0);
-      L.a2[S0] = add2(A1, add2(D2, Dm2));
-      L.b2[S0] = fma2(sub2(ZP2, ZM2), A.k_two, B1);
-      L.q2[S0] = fma2(D2, D2, fma2(Dm2, Dm2, Q1));
+      ring_put<R_A2, S0>(C, L.a2, add2(A1, add2(D2, Dm2)));
+      ring_put<R_B2, S0>(C, L.b2, fma2(sub2(ZP2, ZM2), A.k_two, B1));
+      ring_put<R_Q2, S0>(C, L.q2, fma2(D2, D2, fma2(Dm2, Dm2, Q1)));
     }
   }
   {
@@ -494,7 +517,7 @@ __device__ __forceinline__ void march_step(StepCtx<S>& C, Lane<S>& L, int t, uns
       pmn[r] = mn;
       pmx[r] = mx;
     }
-    L.c1mn[S0] = mk(cmn[0], cmn[1]); L.c1mx[S0] = mk(cmx[0], cmx[1]);
+    ring_put<R_C1MN, S0>(C, L.c1mn, mk(cmn[0], cmn[1])); ring_put<R_C1MX, S0>(C, L.c1mx, mk(cmx[0], cmx[1]));
     L.p1mn[S0] = mk(pmn[0], pmn[1]); L.p1mx[S0] = mk(pmx[0], pmx[1]);
   }
   if (t < 4) return;  // rings not primed yet
@@ -502,6 +525,11 @@ __device__ __forceinline__ void march_step(StepCtx<S>& C, Lane<S>& L, int t, uns
   const unsigned shcol = C.sh_lane + (t & 1) * SHBUF_BYTES;
   {
     float mn2[2], mx2[2];
+    f2 c1mnA = 0ull, c1mnB = 0ull, c1mxA = 0ull, c1mxB = 0ull;
+    if constexpr (S::W11 >= 0) {
+      c1mnA = ring_get<R_C1MN, S1, S0>(C, L.c1mn); c1mnB = ring_get<R_C1MN, S3, S0>(C, L.c1mn);
+      c1mxA = ring_get<R_C1MX, S1, S0>(C, L.c1mx); c1mxB = ring_get<R_C1MX, S3, S0>(C, L.c1mx);
+    }
     f2 TL1 = L.e[S4], TR1 = L.e[S0];
     if constexpr (S::TIP1) {
       const float qn = __int_as_float(0x7fc00000);
@@ -513,8 +541,8 @@ __device__ __forceinline__ void march_step(StepCtx<S>& C, Lane<S>& L, int t, uns
       auto R = [&](f2 v) { return r ? hi(v) : lo(v); };
       float mn = R(L.p1mn[S2]), mx = R(L.p1mx[S2]);
       if constexpr (S::W11 >= 0) {
-        mn = min3n(mn, R(L.c1mn[S1]), R(L.c1mn[S3]));
-        mx = max3n(mx, R(L.c1mx[S1]), R(L.c1mx[S3]));
+        mn = min3n(mn, R(c1mnA), R(c1mnB));
+        mx = max3n(mx, R(c1mxA), R(c1mxB));
       }
       if constexpr (S::W12 == 0 || S::TIP1) {
         const float tl = R(TL1), tr = R(TR1);
@@ -566,34 +594,34 @@ __device__ __forceinline__ void march_step(StepCtx<S>& C, Lane<S>& L, int t, uns
       PC = add2(PC, add2(mk(gtf(lo(SU), A.step_crit), gtf(hi(SU), A.step_crit)), mk(gtf(lo(SD), A.step_crit), gtf(hi(SD), A.step_crit))));
     }
     L.sh[S0] = V0;
-    L.s3mx[S0] = mk(smx[0], smx[1]); L.s3c[S0] = mk(sc[0], sc[1]);
+    ring_put<R_S3MX, S0>(C, L.s3mx, mk(smx[0], smx[1])); ring_put<R_S3C, S0>(C, L.s3c, mk(sc[0], sc[1]));
     L.pcmx[S0] = mk(pmx[0], pmx[1]); L.pcc[S0] = PC;
   }
   // ---- normals / slope / roughness of column jn = ce - 2 (ages: l = 2 - age) -------------------
   const int jn = ce - 2;
   if (jn >= C.q0 && jn < C.q1) {
     const f2 ec = L.e[S2];
-    f2 Sw = runA<S::WN0>(L, S2), Sk = runB<S::WN0>(L, S2), Sww = runQ<S::WN0>(L, S2);
+    f2 Sw = runA<S::WN0, S2, S0>(C, L), Sk = runB<S::WN0, S2, S0>(C, L), Sww = runQ<S::WN0, S2, S0>(C, L);
     f2 Sl = 0ull;
     if constexpr (S::WN1 >= 0) {
       const f2 dR = sub2(L.e[S1], ec), dL = sub2(L.e[S3], ec);
-      const f2 aR = runA<S::WN1>(L, S1), aL = runA<S::WN1>(L, S3);
+      const f2 aR = runA<S::WN1, S1, S0>(C, L), aL = runA<S::WN1, S3, S0>(C, L);
       const f2 tR = fma2(A.k_m1, dR, aR), tL = fma2(A.k_m1, dL, aL);
       Sw = add2(Sw, add2(tR, tL));
       Sl = sub2(tR, tL);
-      Sk = add2(Sk, add2(runB<S::WN1>(L, S1), runB<S::WN1>(L, S3)));
-      Sww = add2(Sww, fma2(dR, add2(aR, tR), runQ<S::WN1>(L, S1)));
-      Sww = add2(Sww, fma2(dL, add2(aL, tL), runQ<S::WN1>(L, S3)));
+      Sk = add2(Sk, add2(runB<S::WN1, S1, S0>(C, L), runB<S::WN1, S3, S0>(C, L)));
+      Sww = add2(Sww, fma2(dR, add2(aR, tR), runQ<S::WN1, S1, S0>(C, L)));
+      Sww = add2(Sww, fma2(dL, add2(aL, tL), runQ<S::WN1, S3, S0>(C, L)));
     }
     if constexpr (S::WN2 >= 0) {
       const f2 dR = sub2(L.e[S0], ec), dL = sub2(L.e[S4], ec);
-      const f2 aR = runA<S::WN2>(L, S0), aL = runA<S::WN2>(L, S4);
+      const f2 aR = runA<S::WN2, S0, S0>(C, L), aL = runA<S::WN2, S4, S0>(C, L);
       const f2 tR = fma2(A.k_m0, dR, aR), tL = fma2(A.k_m0, dL, aL);
       Sw = add2(Sw, add2(tR, tL));
       Sl = fma2(A.k_two, sub2(tR, tL), Sl);
-      Sk = add2(Sk, add2(runB<S::WN2>(L, S0), runB<S::WN2>(L, S4)));
-      Sww = add2(Sww, fma2(dR, add2(aR, tR), runQ<S::WN2>(L, S0)));
-      Sww = add2(Sww, fma2(dL, add2(aL, tL), runQ<S::WN2>(L, S4)));
+      Sk = add2(Sk, add2(runB<S::WN2, S0, S0>(C, L), runB<S::WN2, S4, S0>(C, L)));
+      Sww = add2(Sww, fma2(dR, add2(aR, tR), runQ<S::WN2, S0, S0>(C, L)));
+      Sww = add2(Sww, fma2(dL, add2(aL, tL), runQ<S::WN2, S4, S0>(C, L)));
     }
     // row index grows toward -x and column index toward -y: kp carries that sign and 1/N
     const Normal2 n = finish_normal2(A, Sw, Sk, Sl, Sww, ec);
@@ -616,15 +644,17 @@ __device__ __forceinline__ void march_step(StepCtx<S>& C, Lane<S>& L, int t, uns
       TL2 = add2(TL2, bc((cm_jo & 4u) ? 0.0f : qn));
       TR2 = add2(TR2, bc((cm_jo & 8u) ? 0.0f : qn));
     }
+    f2 s3mxA = 0ull, s3mxB = 0ull;
+    if constexpr (S::W21 >= 0) { s3mxA = ring_get<R_S3MX, S1, S0>(C, L.s3mx); s3mxB = ring_get<R_S3MX, S3, S0>(C, L.s3mx); }
     f2 CNT = L.pcc[S2];
-    if constexpr (S::W21 >= 0) CNT = add2(CNT, add2(L.s3c[S1], L.s3c[S3]));
+    if constexpr (S::W21 >= 0) CNT = add2(CNT, add2(ring_get<R_S3C, S1, S0>(C, L.s3c), ring_get<R_S3C, S3, S0>(C, L.s3c)));
     if constexpr (S::W22 == 0 || S::TIP2)
       CNT = add2(CNT, add2(mk(gtf(lo(TL2), A.step_crit), gtf(hi(TL2), A.step_crit)), mk(gtf(lo(TR2), A.step_crit), gtf(hi(TR2), A.step_crit))));
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
       auto R = [&](f2 x) { return r ? hi(x) : lo(x); };
       float mx = R(L.pcmx[S2]);
-      if constexpr (S::W21 >= 0) mx = max3n(mx, R(L.s3mx[S1]), R(L.s3mx[S3]));
+      if constexpr (S::W21 >= 0) mx = max3n(mx, R(s3mxA), R(s3mxB));
       if constexpr (S::W22 == 0 || S::TIP2) mx = max3n(mx, R(TL2), R(TR2));
       sflag |= (mx > 3.0e38f) ? (1u << r) : 0u;  // an infinite elevation reached the window: the slow path sorts it out
       mx2[r] = mx;
@@ -674,7 +704,8 @@ __global__ void TE_KERNEL_ATTR k_chain_fused(const __grid_constant__ CUtensorMap
   unsigned kglob = 0;  // chunks consumed so far by this warp (stage = kglob % NST, parity = (kglob / NST) & 1)
 
   Lane<S> L;
-  StepCtx<S> C{A, ering + lane * 8u, shbuf + lane * 8u, lane, 0, 0, 0, 0ull, 0ull, 0ull, 0ull, false, 0, 0};
+  StepCtx<S> C{A, ering + lane * 8u, shbuf + lane * 8u, lane, 0, 0, 0, 0ull, 0ull, 0ull, 0ull,
+               reinterpret_cast<f2*>(smem_raw + warp * WARP_SMEM_BYTES + (NST * STAGE_BYTES + 2 * SHBUF_BYTES + 64)) + lane, false, 0, 0};
 
   int unit = gwarp;  // the first unit is static, the rest come from the queue
   while (unit < nunits) {
