@@ -895,8 +895,8 @@ void plan_levels(FusedArgs& a, int out_ncols, int nmaps, int total_warps) {
 
 template <class S, bool KN>
 int launch_shape(FusedState& st, const CUtensorMap& map, const FusedArgs& a, int sms, cudaStream_t s) {
-  static bool attr_set = false;
   const int smem = WARPS_PER_CTA * WARP_SMEM_BYTES;
+  bool& attr_set = st.smem_attr[st.shape_id * 2 + (KN ? 1 : 0)];
   if (!attr_set) {
     if (cudaFuncSetAttribute(k_chain_fused<S, KN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
       st.why = "cudaFuncSetAttribute(max dynamic shared memory) failed";

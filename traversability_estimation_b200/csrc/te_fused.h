@@ -17,6 +17,8 @@ struct FusedState {
   void* d_rowmask = nullptr;  // per-row on-circle membership bits
   void* d_colmask = nullptr;
   size_t rowmask_cap = 0, colmask_cap = 0;
+  bool smem_attr[4] = {false, false, false, false};  // dynamic shared memory limit raised for instantiation [shape*2 + normals]
+                                                     // (a per-device function attribute; a context lives on one device)
   void invalidate() { valid = false; }
   void release();
 };
