@@ -1,4 +1,9 @@
-"""Calibration run: flagged-cell count and fp32 error against the oracle for a sweep of the certification constants (dev tool, GPU)."""
+"""Calibration run: flagged-cell count and fp32 error against the oracle for a sweep of the certification constants (dev tool, GPU).
+
+Needs a calibration build, which is the only one that reads TE_FUSED_ROUGH_K / TE_FUSED_COND_K:
+    make -C traversability_estimation_b200/csrc variant NAME=calib EXTRA=-DTE_CALIBRATION=1
+    TE_B200_LIBRARY=$PWD/traversability_estimation_b200/libte_b200_calib.so python tools/dev_calib.py
+"""
 import os, sys, json
 sys.path.insert(0, '/root/repo'); sys.path.insert(0, '/root/repo/tools'); sys.path.insert(0, '/root/repo/tests')
 import numpy as np, synth, torch, bench

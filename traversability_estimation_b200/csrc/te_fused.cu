@@ -1042,10 +1042,12 @@ int launch_chain_fused(FusedState& st, const SlabView& v, const ChainDev& p, int
   const double N = wn.n, K2 = wn.k2;
   a.a_cov = (float)(res * res * K2 / N);
   a.half_a = 0.5f * a.a_cov;
-  // certification constants (DESIGN.md "certification"); env overrides exist for calibration runs only
+  // certification constants (DESIGN.md "certification")
   double rough_k = 0.06, cond_k = 0.25;
+#ifdef TE_CALIBRATION  // calibration builds only (tools/dev_calib.py): the shipped library does not take its certification from the environment
   if (const char* e = std::getenv("TE_FUSED_ROUGH_K")) rough_k = std::atof(e);
   if (const char* e = std::getenv("TE_FUSED_COND_K")) cond_k = std::atof(e);
+#endif
   a.cond_k = (float)cond_k;
   a.rough_thr = (float)((rough_k / p.rough_crit) * (rough_k / p.rough_crit) * (N - 1.0) / N);
   a.kp = (float)(-res / N);
