@@ -116,7 +116,9 @@ int te_get_stats(te_ctx* ctx, int64_t* kernel_launches, int64_t* slow_path_cells
 int te_enable_timing(te_ctx* ctx, int on);
 int te_get_timing(te_ctx* ctx, double* main_ms, double* fixup_ms, int64_t* samples);
 /* Work-list counters of the last fused launch: [0] cells the fp32 stencil could not certify (tier 2,
- * fp64 on centred coordinates); [4] cells tier 2 passed on to the literal kernel (tier 3); [1..3] reserved (0). */
+ * fp64 on centred coordinates); [1] work-list entries reserved for them (warp-private chunks, padding included);
+ * [2] non-zero if a work list overflowed (cannot happen: the lists are sized for every cell of the launch);
+ * [4] cells tier 2 passed on to the literal kernel (tier 3); [3] reserved (0). */
 int te_get_flag_counters(te_ctx* ctx, uint32_t out[5]);
 /* Work decomposition the fused kernel uses for `nmaps` maps of rows x out_ncols output cells on a GPU with `sms`
  * multiprocessors (host arithmetic only, needs no GPU; no reference counterpart — the reference iterates cell by cell).

@@ -13,7 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def test_plan_covers_map_without_overlap():
     from traversability_estimation_b200.sharding import plan_slab
-    for cols, world, halo in ((8192, 8, 4), (133, 3, 4), (10, 4, 41), (64, 1, 4)):
+    for cols, world, halo in ((8192, 8, 4), (133, 3, 4), (200, 4, 41), (64, 1, 4)):
         plans = [plan_slab(cols, world, r, halo) for r in range(world)]
         assert plans[0].col_begin == 0 and plans[0].halo_left == 0 and plans[-1].halo_right == 0
         assert sum(p.col_count for p in plans) == cols
@@ -22,6 +22,16 @@ def test_plan_covers_map_without_overlap():
         for p in plans:
             assert p.halo_left == min(halo, p.col_begin)
             assert p.halo_right == min(halo, cols - p.col_begin - p.col_count)
+
+
+def test_plan_rejects_slabs_narrower_than_the_halo():
+    """The halo exchange is one hop: a rank that owns fewer columns than the halo cannot serve its neighbour."""
+    from traversability_estimation_b200.sharding import plan_slab
+    with pytest.raises(ValueError, match="narrower than the halo"):
+        plan_slab(10, 4, 1, 41)
+    with pytest.raises(ValueError, match="narrower than the halo"):
+        plan_slab(8192, 8, 0, 1025)
+    plan_slab(10, 1, 0, 41)  # a single rank exchanges nothing
 
 
 WORKER = textwrap.dedent("""

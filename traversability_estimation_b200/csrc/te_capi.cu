@@ -91,7 +91,8 @@ struct te_ctx {
   cudaStream_t s_h2d = nullptr, s_d2h = nullptr;  // te_chain(TE_MEM_HOST) pipeline
   bool timing = false;
   struct Ev3 { cudaEvent_t a, b, c; };
-  std::vector<Ev3> events;
+  std::vector<Ev3> events;   // timing events, created once and reused (te_get_timing rewinds events_used)
+  size_t events_used = 0;
 };
 
 namespace {
@@ -227,47 +228,67 @@ int launch_check(te_ctx* c, const char* what) {
   return TE_OK;
 }
 
+// The next triple of timing events; the pool grows on demand and is reused after te_get_timing.
+int next_timing_slot(te_ctx* c, te_ctx::Ev3** out) {
+  if (c->events_used == c->events.size()) {
+    te_ctx::Ev3 ev{};
+    TE_CUDA(cudaEventCreate(&ev.a)); TE_CUDA(cudaEventCreate(&ev.b)); TE_CUDA(cudaEventCreate(&ev.c));
+    c->events.push_back(ev);
+  }
+  *out = &c->events[c->events_used];
+  return TE_OK;
+}
+
 // Device-memory chain on one slab: picks the kernel.
 int run_chain_device(te_ctx* c, const te_geometry* g, const te::SlabView& v, const te_chain_params* p, const float* elev,
                      const te::ChainOut& o, int nmaps) {
   const te::ChainDev d = make_chain_dev(g, p);
   bool use_fused = false;
   if (c->kernel_choice != TE_KERNEL_GENERIC) {
-    use_fused = te::fused_eligible(c->fused, c->hX, c->hY, g, p);
+    use_fused = te::fused_eligible(c->fused, c->hX, c->hY, g, p, c->stream);
     if (!use_fused && c->kernel_choice == TE_KERNEL_FUSED)
       return fail(TE_ERR_UNSUPPORTED, "fused stencil has no instantiation for these window shapes: %s", c->fused.why.c_str());
+    if (use_fused) {
+      if (const char* why = te::fused_launch_obstacle(v, nmaps, elev, o)) {
+        if (c->kernel_choice == TE_KERNEL_FUSED) return fail(TE_ERR_UNSUPPORTED, "fused stencil cannot run this launch: %s", why);
+        use_fused = false;  // TE_KERNEL_AUTO: the generic kernel computes the same layers
+      }
+    }
   }
   const size_t in_stride = (size_t)g->rows * v.in_ncols, out_stride = (size_t)g->rows * v.out_ncols;
   if (use_fused) {
-    const unsigned cap = (unsigned)std::min<size_t>(out_stride * (size_t)nmaps, (size_t)1 << 26);
-    TE_CUDA(c->worklist.reserve(sizeof(unsigned) * (size_t)cap));
-    TE_CUDA(c->worklist3.reserve(sizeof(unsigned) * (size_t)cap));
+    // The work lists hold every cell of the launch (plus chunk padding), so they cannot overflow: a degenerate map (exact planes,
+    // holes everywhere) sends all of its cells down the certified slow path instead of returning uncertified fp32 values.
+    const size_t cells = out_stride * (size_t)nmaps;
+    const size_t cap = te::fused_list_capacity(cells, c->sms);
+    if (cap >= ((size_t)1 << 32)) return fail(TE_ERR_UNSUPPORTED, "launch of %zu cells exceeds the work-list index range", cells);
+    TE_CUDA(c->worklist.reserve(sizeof(unsigned) * cap));
+    TE_CUDA(c->worklist3.reserve(sizeof(unsigned) * cells));
     TE_CUDA(c->counter.reserve(sizeof(unsigned) * 64));
     {  // one launch covers every map of the batch
       const te::ChainOut& om = o;
-      const int m = 0;
       TE_CUDA(cudaMemsetAsync(c->counter.p, 0, sizeof(unsigned) * 64, c->stream));
-      te_ctx::Ev3 ev{};
+      te_ctx::Ev3* ev = nullptr;
       if (c->timing) {
-        TE_CUDA(cudaEventCreate(&ev.a)); TE_CUDA(cudaEventCreate(&ev.b)); TE_CUDA(cudaEventCreate(&ev.c));
-        TE_CUDA(cudaEventRecord(ev.a, c->stream));
+        if (int rc = next_timing_slot(c, &ev)) return rc;
+        TE_CUDA(cudaEventRecord(ev->a, c->stream));
       }
-      int rc = te::launch_chain_fused(c->fused, v, d, nmaps, elev + m * in_stride, om, (unsigned*)c->worklist.p,
-                                      (unsigned*)c->counter.p, cap, c->sms, c->stream);
+      int rc = te::launch_chain_fused(c->fused, v, d, nmaps, elev, om, (unsigned*)c->worklist.p, (unsigned*)c->counter.p,
+                                      (unsigned)cap, c->sms, c->stream);
       if (rc != 0) return fail(TE_ERR_CUDA, "fused chain launch failed: %s", c->fused.why.c_str());
       if (int r2 = launch_check(c, "k_chain_fused")) return r2;
-      if (c->timing) TE_CUDA(cudaEventRecord(ev.b, c->stream));
+      if (c->timing) TE_CUDA(cudaEventRecord(ev->b, c->stream));
       te::FixupArgs fa;
       te::make_fixup_args(c->fused, v, d, &fa);
-      te::launch_fixup_t2(fa, elev + m * in_stride, om, (const unsigned*)c->worklist.p, (const unsigned*)c->counter.p, cap,
-                          (unsigned*)c->worklist3.p, (unsigned*)c->counter.p + 4, c->sms, c->stream);
+      te::launch_fixup_t2(fa, elev, om, (const unsigned*)c->worklist.p, (const unsigned*)c->counter.p, (unsigned)cap,
+                          (unsigned*)c->worklist3.p, (unsigned*)c->counter.p + 4, (unsigned)cells, c->sms, c->stream);
       if (int r2 = launch_check(c, "k_fixup_t2")) return r2;
-      te::launch_fixup(v, d, elev + m * in_stride, om, (const unsigned*)c->worklist3.p, (const unsigned*)c->counter.p + 4, cap, c->sms,
+      te::launch_fixup(v, d, elev, om, (const unsigned*)c->worklist3.p, (const unsigned*)c->counter.p + 4, (unsigned)cells, c->sms,
                        c->stream);
       if (int r2 = launch_check(c, "k_fixup_cells")) return r2;
       if (c->timing) {
-        TE_CUDA(cudaEventRecord(ev.c, c->stream));
-        c->events.push_back(ev);
+        TE_CUDA(cudaEventRecord(ev->c, c->stream));
+        ++c->events_used;
       }
     }
   } else {
@@ -277,17 +298,17 @@ int run_chain_device(te_ctx* c, const te_geometry* g, const te::SlabView& v, con
       if (om.nx) om.nx += m * out_stride;
       if (om.ny) om.ny += m * out_stride;
       if (om.nz) om.nz += m * out_stride;
-      te_ctx::Ev3 ev{};
+      te_ctx::Ev3* ev = nullptr;
       if (c->timing) {
-        TE_CUDA(cudaEventCreate(&ev.a)); TE_CUDA(cudaEventCreate(&ev.b)); TE_CUDA(cudaEventCreate(&ev.c));
-        TE_CUDA(cudaEventRecord(ev.a, c->stream));
+        if (int rc = next_timing_slot(c, &ev)) return rc;
+        TE_CUDA(cudaEventRecord(ev->a, c->stream));
       }
       te::launch_chain_generic(v, d, elev + m * in_stride, om, c->sms, c->stream);
       if (int r2 = launch_check(c, "k_chain_generic")) return r2;
       if (c->timing) {
-        TE_CUDA(cudaEventRecord(ev.b, c->stream));
-        TE_CUDA(cudaEventRecord(ev.c, c->stream));
-        c->events.push_back(ev);
+        TE_CUDA(cudaEventRecord(ev->b, c->stream));
+        TE_CUDA(cudaEventRecord(ev->c, c->stream));
+        ++c->events_used;
       }
     }
   }
@@ -343,6 +364,7 @@ int te_destroy(te_ctx* c) {
       c->counter.release();
       c->fused.release();
       c->fp.release();
+      for (auto& e : c->events) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); cudaEventDestroy(e.c); }
       if (c->s_h2d) cudaStreamDestroy(c->s_h2d);
       if (c->s_d2h) cudaStreamDestroy(c->s_d2h);
       if (c->own_stream) cudaStreamDestroy(c->own_stream);
@@ -381,7 +403,7 @@ int te_get_stats(te_ctx* c, int64_t* launches, int64_t* slow) {
       TE_CUDA(cudaStreamSynchronize(c->stream));
       TE_CUDA(cudaMemcpy(last, c->counter.p, sizeof(last), cudaMemcpyDeviceToHost));
     }
-    *slow = (int64_t)last[0];
+    *slow = (int64_t)last[1];  // cells flagged (word 0 counts reserved list entries, chunk padding included)
   }
   return TE_OK;
 }
@@ -396,18 +418,18 @@ int te_get_timing(te_ctx* c, double* main_ms, double* fixup_ms, int64_t* samples
   TE_ENTER(c);
   TE_CUDA(cudaStreamSynchronize(c->stream));
   double m = 0.0, f = 0.0;
-  for (auto& e : c->events) {
+  for (size_t k = 0; k < c->events_used; ++k) {
+    const auto& e = c->events[k];
     float t1 = 0.f, t2 = 0.f;
     TE_CUDA(cudaEventElapsedTime(&t1, e.a, e.b));
     TE_CUDA(cudaEventElapsedTime(&t2, e.b, e.c));
     m += t1;
     f += t2;
-    cudaEventDestroy(e.a); cudaEventDestroy(e.b); cudaEventDestroy(e.c);
   }
   if (main_ms) *main_ms = m;
   if (fixup_ms) *fixup_ms = f;
-  if (samples) *samples = (int64_t)c->events.size();
-  c->events.clear();
+  if (samples) *samples = (int64_t)c->events_used;
+  c->events_used = 0;
   return TE_OK;
 }
 
@@ -424,8 +446,13 @@ int te_get_flag_counters(te_ctx* c, uint32_t out[5]) {
   if (!out) return fail(TE_ERR_BAD_ARG, "null argument");
   for (int k = 0; k < 5; ++k) out[k] = 0;
   if (c->counter.p) {
+    unsigned raw[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     TE_CUDA(cudaStreamSynchronize(c->stream));
-    TE_CUDA(cudaMemcpy(out, c->counter.p, 20, cudaMemcpyDeviceToHost));
+    TE_CUDA(cudaMemcpy(raw, c->counter.p, sizeof(raw), cudaMemcpyDeviceToHost));
+    out[0] = raw[1];            // cells flagged by the fp32 stencil
+    out[1] = raw[0];            // list entries reserved (warp-private chunks, padding included)
+    out[2] = raw[2] | raw[5];   // a work list overflowed (never: the lists hold every cell of the launch)
+    out[4] = raw[4];            // cells tier 2 passed on to the literal kernel
   }
   return TE_OK;
 }
@@ -562,13 +589,29 @@ static int chain_host_pipelined(te_ctx* c, const te_geometry* g, const te_slab& 
   if (!c->s_d2h) TE_CUDA(cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking));
   const int nchunk = std::min(16, std::max(2, s.col_count / 512));
   const int chunk = (s.col_count + nchunk - 1) / nchunk;
+  // events and the drain of the three streams are released on every exit path
+  struct Pipeline {
+    te_ctx* c;
+    std::vector<cudaEvent_t> ev;
+    cudaError_t make(cudaEvent_t* out) {
+      cudaError_t e = cudaEventCreateWithFlags(out, cudaEventDisableTiming);
+      if (e == cudaSuccess) ev.push_back(*out);
+      return e;
+    }
+    ~Pipeline() {
+      cudaStreamSynchronize(c->s_h2d);
+      cudaStreamSynchronize(c->stream);
+      cudaStreamSynchronize(c->s_d2h);
+      for (cudaEvent_t e : ev) cudaEventDestroy(e);
+    }
+  } pipe{c, {}};
   std::vector<cudaEvent_t> up(nchunk), done(nchunk);
   for (int k = 0; k < nchunk; ++k) {
-    TE_CUDA(cudaEventCreateWithFlags(&up[k], cudaEventDisableTiming));
-    TE_CUDA(cudaEventCreateWithFlags(&done[k], cudaEventDisableTiming));
+    TE_CUDA(pipe.make(&up[k]));
+    TE_CUDA(pipe.make(&done[k]));
   }
   cudaEvent_t start;
-  TE_CUDA(cudaEventCreateWithFlags(&start, cudaEventDisableTiming));
+  TE_CUDA(pipe.make(&start));
   TE_CUDA(cudaEventRecord(start, c->stream));  // order after whatever the caller queued on the context stream
   TE_CUDA(cudaStreamWaitEvent(c->s_h2d, start, 0));
   TE_CUDA(cudaStreamWaitEvent(c->s_d2h, start, 0));
@@ -609,8 +652,6 @@ static int chain_host_pipelined(te_ctx* c, const te_geometry* g, const te_slab& 
   cudaStreamSynchronize(c->s_h2d);
   cudaStreamSynchronize(c->stream);
   cudaError_t e = cudaStreamSynchronize(c->s_d2h);
-  for (int k = 0; k < nchunk; ++k) { cudaEventDestroy(up[k]); cudaEventDestroy(done[k]); }
-  cudaEventDestroy(start);
   if (rc == TE_OK && e != cudaSuccess) rc = fail(TE_ERR_CUDA, "pipelined chain failed: %s", cudaGetErrorString(e));
   return rc;
 }

@@ -241,11 +241,12 @@ __device__ bool normals_t2(const FixupArgs& A, const Elev& E, int i, int j, floa
 
 __global__ void __launch_bounds__(128, 6) k_fixup_t2(FixupArgs A, const float* __restrict__ elev, ChainOut o,
                                                   const unsigned* __restrict__ list, const unsigned* __restrict__ count,
-                                                  unsigned cap, unsigned* list3, unsigned* count3) {
+                                                  unsigned cap, unsigned* list3, unsigned* count3, unsigned cap3) {
   unsigned n = *count;
   if (n > cap) n = cap;
   for (unsigned k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
     const unsigned w = list[k];
+    if (w == LIST_INVALID) continue;  // padding of a warp's chunk tail
     const unsigned c = w & 0x3fffffffu;
     const unsigned mapi = c / A.map_cells, cl = c - mapi * A.map_cells;
     const int i = (int)(cl % (unsigned)A.rows);
@@ -275,7 +276,8 @@ __global__ void __launch_bounds__(128, 6) k_fixup_t2(FixupArgs A, const float* _
     }
     if (escalate) {
       const unsigned idx = atomicAdd(count3, 1u);
-      if (idx < cap) list3[idx] = c | (1u << 30);  // tier 3 redoes the normals part and re-fuses
+      if (idx < cap3) list3[idx] = c | (1u << 30);  // tier 3 redoes the normals part and re-fuses
+      else atomicExch(count3 + 1, 1u);              // cannot happen: list3 holds every cell of the launch
     } else {
       o.trav[c] = __fmul_rn(A.fuse_w, __fadd_rn(__fadd_rn(s, t), r));
     }
@@ -285,8 +287,8 @@ __global__ void __launch_bounds__(128, 6) k_fixup_t2(FixupArgs A, const float* _
 }  // namespace
 
 void launch_fixup_t2(const FixupArgs& a, const float* elev, const ChainOut& o, const unsigned* list, const unsigned* count,
-                     unsigned cap, unsigned* list3, unsigned* count3, int sms, cudaStream_t s) {
-  k_fixup_t2<<<sms * 64, 128, 0, s>>>(a, elev, o, list, count, cap, list3, count3);  // ~1.2 M threads: one listed cell each, latency hidden by occupancy
+                     unsigned cap, unsigned* list3, unsigned* count3, unsigned cap3, int sms, cudaStream_t s) {
+  k_fixup_t2<<<sms * 64, 128, 0, s>>>(a, elev, o, list, count, cap, list3, count3, cap3);  // ~1.2 M threads: one listed cell each, latency hidden by occupancy
 }
 
 }  // namespace te

@@ -52,6 +52,19 @@ constexpr int SHBUF_BYTES = 288;   // 2 pad + 64 + 2 pad floats, padded
 #define TE_SMEM_RINGS 1
 #endif
 constexpr bool SMEM_RINGS = TE_SMEM_RINGS != 0;
+// TE_STRAIGHT=1: a march step is one straight basic block — every stage runs on every step (the warm-up and drain steps of a
+// unit compute on whatever the rings hold) and only the stores and the work-list append are predicated, so ptxas can interleave
+// the four independent dependency chains of a step (arriving column, step_height, normals, step layer).
+#ifndef TE_STRAIGHT
+#define TE_STRAIGHT 0
+#endif
+constexpr bool STRAIGHT = TE_STRAIGHT != 0;
+// TE_RING_REG1: bit mask of shared-memory rings (RingId) whose age-1 read comes from the register the value was put in one
+// step earlier instead of from shared memory (one more live register pair per ring, one LDS.64 less per step).
+#ifndef TE_RING_REG1
+#define TE_RING_REG1 0
+#endif
+constexpr unsigned RING_REG1 = TE_RING_REG1;
 enum RingId { R_A1, R_B1, R_Q1, R_A2, R_B2, R_Q2, R_C1MN, R_C1MX, R_S3MX, R_S3C, NRING };
 constexpr int RING_BYTES = SMEM_RINGS ? NRING * 5 * 32 * 8 : 0;
 constexpr int WARP_SMEM_BYTES = NST * STAGE_BYTES + 2 * SHBUF_BYTES + 64 + RING_BYTES;  // 6272 = 49 * 128 (+ 12800 = 100 * 128)
@@ -67,6 +80,7 @@ constexpr int WARPS_PER_CTA = TE_WPC;
 constexpr unsigned FULL = 0xffffffffu;
 
 constexpr int NLVL = 4;            // levels of the work queue
+constexpr unsigned LIST_CHUNK = 512u;  // work-list entries a warp reserves at a time (an append adds at most 64)
 
 typedef unsigned long long f2;  // two packed floats in one aligned register pair (see below)
 
@@ -89,9 +103,10 @@ struct FusedArgs {
   float invN;       // 1 / N
   float n_over_nm1; // N / (N-1)
   float rough_thr;  // (0.2 / crit_rough)^2 * (N-1)/N : lambda0 below rough_thr*cmag^2 cannot be certified
-  float slope_crit, inv_slope_crit;
-  float step_crit, inv_step_crit, inv_ncrit;
-  float rough_crit, inv_rough_crit;
+  float slope_crit, inv_slope_crit, minv_slope_crit;
+  float step_crit, inv_step_crit, minv_step_crit, inv_ncrit;
+  float step_cmp;   // largest float <= critical step (double): `h > step_cmp` in float == `(double)h > critical` (StepFilter.cpp:165)
+  float rough_crit, inv_rough_crit, minv_rough_crit;
   float fuse_w;
   float cond_k;     // eigen-gap / scale ratio below which the fp32 eigenvector is not trusted
   // constants pre-broadcast to both halves of a register pair (one LDC.64 each)
@@ -173,6 +188,12 @@ __device__ __forceinline__ float min3n(float a, float b, float c) {
 __device__ __forceinline__ float gtf(float a, float b) {
   float r;
   asm("set.gt.f32.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+  return r;
+}
+// max(fma(a, b, 1), 0) for a*b <= 0 in one instruction (FFMA.SAT clamps to [0, 1]; NaN -> +0 exactly like fmaxf(NaN, 0))
+__device__ __forceinline__ float fma_sat1(float a, float b) {
+  float r;
+  asm("fma.rn.sat.f32 %0, %1, %2, 0f3F800000;" : "=f"(r) : "f"(a), "f"(b));
   return r;
 }
 __device__ __forceinline__ float rcp_a(float x) {
@@ -291,7 +312,8 @@ __device__ __forceinline__ void ring_put(const CT& C, f2 (&reg)[5], f2 v) {
 }
 template <int RID, int SLOT, int S0, class CT>
 __device__ __forceinline__ f2 ring_get(const CT& C, const f2 (&reg)[5]) {
-  if constexpr (SMEM_RINGS && SLOT != S0) return C.rg[(RID * 5 + SLOT) * 32];
+  constexpr bool age1_in_reg = ((RING_REG1 >> RID) & 1u) != 0u && SLOT == (S0 + 4) % 5;
+  if constexpr (SMEM_RINGS && SLOT != S0 && !age1_in_reg) return C.rg[(RID * 5 + SLOT) * 32];
   else return reg[SLOT];
 }
 template <int W, int SLOT, int S0, class CT, class S>
@@ -388,8 +410,8 @@ __device__ __forceinline__ Normal2 finish_normal2(const FusedArgs& A, f2 Sw, f2 
   // holes (invalid centre) need no second opinion.
   const f2 lbase = fma2(cmag, A.k_1em5, A.k_1em10a);
   const f2 t1 = sub2(lam0, mk(fmaxf(lo(lbase), lo(thr)), fmaxf(hi(lbase), hi(thr))));
-  const f2 D2 = add2(D, D);
-  const f2 t2 = fma2(mk(fmaxf(A.a_cov, lo(c)), fmaxf(A.a_cov, hi(c))), A.k_mcond, mk(fminf(lo(D2), lo(m)), fminf(hi(D2), hi(m))));
+  // the eigen-gap is min(2D, a - lambda0) = a - lambda0 = m: m = D + h <= 2D because D = sqrt(h^2 + g^2) >= |h|
+  const f2 t2 = fma2(mk(fmaxf(A.a_cov, lo(c)), fmaxf(A.a_cov, hi(c))), A.k_mcond, m);
   const f2 inval = sub2(ec, ec);
   unsigned flag = 0;
   {
@@ -413,36 +435,60 @@ __device__ __forceinline__ Normal2 finish_normal2(const FusedArgs& A, f2 Sw, f2 
     if (cy && fabsf(hi(dist)) <= hi(bound)) flag |= 2u;
   }
   const f2 theta = acos2(A, nz);
-  // layer = x < crit ? 1 - x/crit : 0  ==  max(1 - x/crit, 0)
-  const f2 sl = fma2(theta, A.k_minv_slope, A.k_one);
-  const f2 ro = fma2(r, A.k_minv_rough, A.k_one);
+  // layer = x < crit ? 1 - x/crit : 0  ==  max(1 - x/crit, 0)  ==  sat(1 - x/crit) for x >= 0
   // a hole (invalid centre: NaN, or Inf - Inf) has no normal: slope and roughness stay NaN
   // (SlopeFilter.cpp:71, RoughnessFilter.cpp:84) and the cell is not flagged
   o.nz = add2(nz, inval);
-  o.slope = add2(mk(fmaxf(lo(sl), 0.0f), fmaxf(hi(sl), 0.0f)), inval);
-  o.rough = add2(mk(fmaxf(lo(ro), 0.0f), fmaxf(hi(ro), 0.0f)), inval);
+  o.slope = add2(mk(fma_sat1(lo(theta), A.minv_slope_crit), fma_sat1(hi(theta), A.minv_slope_crit)), inval);
+  o.rough = add2(mk(fma_sat1(lo(r), A.minv_rough_crit), fma_sat1(hi(r), A.minv_rough_crit)), inval);
   o.flag = flag;
   return o;
 }
 
 // Rare paths kept out of line so that the five unrolled march phases stay small.
-__device__ __noinline__ void append_flagged(unsigned* count, unsigned* list, unsigned cap, int lane, unsigned cell, unsigned fl) {
+//
+// Work-list append.  A warp owns a private chunk of LIST_CHUNK list entries at a time and fills it without atomics; only when an
+// append does not fit into what is left of the chunk does lane 0 reserve the next chunk from the global cursor (count[0]) — one
+// returning atomic per ~LIST_CHUNK flagged cells instead of one per flagged march step, so the march does not wait on L2 atomics.
+// The unused tail of a chunk is padded with LIST_INVALID, which the consumers skip; count[1] tallies the flagged cells themselves
+// (fire-and-forget reduction).  The chunk cursor of a warp lives in its shared-memory block (warp-uniform, rare path).
+__device__ __noinline__ void append_flagged(unsigned* count, unsigned* list, unsigned cap, unsigned lstate, int lane, unsigned cell,
+                                            unsigned fl) {
   const unsigned fl0 = (fl & 1u) | ((fl >> 1) & 2u), fl1 = ((fl >> 1) & 1u) | ((fl >> 2) & 2u);  // per row: bit0 normals, bit1 step
   const unsigned b0 = __ballot_sync(FULL, fl0 != 0u), b1 = __ballot_sync(FULL, fl1 != 0u);
-  unsigned base = 0;
-  if (lane == 0) base = atomicAdd(count, (unsigned)(__popc(b0) + __popc(b1)));
-  base = __shfl_sync(FULL, base, 0);
+  const unsigned n = (unsigned)(__popc(b0) + __popc(b1));
+  unsigned base, pos;
+  asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(base), "=r"(pos) : "r"(lstate) : "memory");
+  if (pos + n > LIST_CHUNK) {  // also the first append of a warp (pos starts at LIST_CHUNK)
+    for (unsigned i = pos + lane; i < LIST_CHUNK; i += 32) list[base + i] = LIST_INVALID;
+    if (lane == 0) base = atomicAdd(count, LIST_CHUNK);
+    base = __shfl_sync(FULL, base, 0);
+    pos = 0;
+    if (base + LIST_CHUNK > cap) {  // cannot happen with the capacity fused_list_capacity() prescribes; never write past the list
+      if (lane == 0) {
+        atomicExch(count + 2, 1u);
+        asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(lstate), "r"(0u), "r"(LIST_CHUNK) : "memory");
+      }
+      __syncwarp();
+      return;
+    }
+  }
   const unsigned lower = (1u << lane) - 1u;
-  if (fl0) {
-    const unsigned idx = base + __popc(b0 & lower);
-    if (idx < cap) list[idx] = cell | (fl0 << 30);
+  if (fl0) list[base + pos + __popc(b0 & lower)] = cell | (fl0 << 30);
+  if (fl1) list[base + pos + __popc(b0) + __popc(b1 & lower)] = (cell + 1u) | (fl1 << 30);
+  if (lane == 0) {
+    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(lstate), "r"(base), "r"(pos + n) : "memory");
+    atomicAdd(count + 1, n);  // result unused: a reduction
   }
-  if (fl1) {
-    const unsigned idx = base + __popc(b0) + __popc(b1 & lower);
-    if (idx < cap) list[idx] = (cell + 1u) | (fl1 << 30);
-  }
+  __syncwarp();
 }
-__device__ __noinline__ void store_normals(float* pnx, float* pny, float* pnz, bool ok, size_t oc, f2 nx, f2 ny, f2 nz) {
+// End of a warp's work: pad what is left of its chunk.
+__device__ __noinline__ void finish_list(unsigned* list, unsigned lstate, int lane) {
+  unsigned base, pos;
+  asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(base), "=r"(pos) : "r"(lstate) : "memory");
+  for (unsigned i = pos + lane; i < LIST_CHUNK; i += 32) list[base + i] = LIST_INVALID;
+}
+__device__ __noinline__ void store_normals(float* pnx, float* pny, float* pnz, bool ok, unsigned oc, f2 nx, f2 ny, f2 nz) {
   if (!ok) return;
   *reinterpret_cast<f2*>(pnx + oc) = nx;
   *reinterpret_cast<f2*>(pny + oc) = ny;
@@ -460,9 +506,11 @@ struct StepCtx {
   f2 tipU1, tipD1;    // pass-1 row tips: +0.0 where the on-circle offset (-2,0)/(+2,0) belongs to the window, NaN where not
   f2 tipU2, tipD2;    // same for pass 2
   f2* rg;             // SMEM_RINGS: the lane's element of ring 0 / slot 0 in shared memory (rings are 32 lanes x 8 bytes apart)
+  unsigned lstate;    // shared address of the warp's work-list cursor {chunk base, entries used}
   bool out_ok;        // lane produces output rows (lanes 1..30 and inside the map)
-  size_t oc;          // running output offset (column jo, lane's first row)
-  size_t ocn;         // same for the normals stage (column jn)
+  unsigned oc;        // running output element offset (column jo, lane's first row); a launch covers < 2^30 cells.  It runs
+                      // 8 columns ahead of the first store of a unit (wraps below zero; never dereferenced then)
+  int len;            // output columns of the unit (q1 - q0)
 };
 
 // One march step: column ce = q0 - 4 + t arrives.  PH = t % 5.
@@ -471,6 +519,8 @@ __device__ __forceinline__ void march_step(StepCtx<S>& C, Lane<S>& L, int t, uns
   const FusedArgs& A = C.A;
   constexpr int S0 = PH, S1 = (PH + 4) % 5, S2 = (PH + 3) % 5, S3 = (PH + 2) % 5, S4 = (PH + 1) % 5;  // slot of age 0..4
   const int ce = C.q0 - 4 + t;
+  const unsigned oc = C.oc;  // element offset of column jo = ce - 4, lane's first row
+  C.oc += (unsigned)A.rows;
   // ---- stage A: the arriving elevation column -------------------------------------------------
   float z[6];
   f2 ZM2, Z0, ZP2;
@@ -479,12 +529,12 @@ __device__ __forceinline__ void march_step(StepCtx<S>& C, Lane<S>& L, int t, uns
     ZM2 = lds64(a); Z0 = lds64(a + 8); ZP2 = lds64(a + 16);
     z[0] = lo(ZM2); z[1] = hi(ZM2); z[2] = lo(Z0); z[3] = hi(Z0); z[4] = lo(ZP2); z[5] = hi(ZP2);
   }
-  const f2 ZM1 = mk(z[1], z[2]), ZP1 = mk(z[3], z[4]);
   L.e[S0] = Z0;
   if constexpr (S::NEED_N1 || S::NEED_N2) {
-    const f2 D1 = sub2(ZP1, Z0), Dm1 = sub2(ZM1, Z0);
+    // the row pairs (z1,z2) and (z3,z4) straddle two registers pairs: scalar subtractions land in aligned pairs without moves
+    const f2 D1 = mk(__fsub_rn(z[3], z[2]), __fsub_rn(z[4], z[3])), Dm1 = mk(__fsub_rn(z[1], z[2]), __fsub_rn(z[2], z[3]));
     const f2 A1 = add2(D1, Dm1);
-    const f2 B1 = sub2(ZP1, ZM1);
+    const f2 B1 = mk(__fsub_rn(z[3], z[1]), __fsub_rn(z[4], z[2]));
     const f2 Q1 = fma2(D1, D1, mul2(Dm1, Dm1));
     if constexpr (S::NEED_N1) { ring_put<R_A1, S0>(C, L.a1, A1); ring_put<R_B1, S0>(C, L.b1, B1); ring_put<R_Q1, S0>(C, L.q1, Q1); }
     if constexpr (S::NEED_N2) {
@@ -520,9 +570,12 @@ __device__ __forceinline__ void march_step(StepCtx<S>& C, Lane<S>& L, int t, uns
     ring_put<R_C1MN, S0>(C, L.c1mn, mk(cmn[0], cmn[1])); ring_put<R_C1MX, S0>(C, L.c1mx, mk(cmx[0], cmx[1]));
     L.p1mn[S0] = mk(pmn[0], pmn[1]); L.p1mx[S0] = mk(pmx[0], pmx[1]);
   }
-  if (t < 4) return;  // rings not primed yet
+  if constexpr (!STRAIGHT) {
+    if (t < 4) return;  // rings not primed yet
+  }
   // ---- stage B: step_height of column js = ce - 2 (ages: js+1 -> 1, js -> 2, js-1 -> 3) ---------
   const unsigned shcol = C.sh_lane + (t & 1) * SHBUF_BYTES;
+  f2 V0;
   {
     float mn2[2], mx2[2];
     f2 c1mnA = 0ull, c1mnB = 0ull, c1mxA = 0ull, c1mxB = 0ull;
@@ -554,19 +607,18 @@ __device__ __forceinline__ void march_step(StepCtx<S>& C, Lane<S>& L, int t, uns
     }
     // centre gate (StepFilter.cpp:113): an invalid centre (NaN, or Inf: Inf - Inf) leaves step_height NaN
     const f2 zc = L.e[S2];
-    sts64(shcol + 8, add2(sub2(mk(mx2[0], mx2[1]), mk(mn2[0], mn2[1])), sub2(zc, zc)));  // buffer row 0 is strip row -2
+    V0 = add2(sub2(mk(mx2[0], mx2[1]), mk(mn2[0], mn2[1])), sub2(zc, zc));
+    sts64(shcol + 8, V0);  // buffer row 0 is strip row -2
   }
   __syncwarp();
   float v[6], f[6];
-  f2 V0;
   f2 SU = 0ull, SD = 0ull;
   {
     const f2 VM2 = lds64(shcol), VP2 = lds64(shcol + 16);
-    V0 = lds64(shcol + 8);
     if constexpr (S::TIP2) { SU = add2(VM2, C.tipU2); SD = add2(VP2, C.tipD2); }
     v[0] = lo(VM2); v[1] = hi(VM2); v[2] = lo(V0); v[3] = hi(V0); v[4] = lo(VP2); v[5] = hi(VP2);
 #pragma unroll
-    for (int k = 0; k < 6; ++k) f[k] = gtf(v[k], A.step_crit);
+    for (int k = 0; k < 6; ++k) f[k] = gtf(v[k], A.step_cmp);
   }
   {
     float smx[2], pmx[2], sc[2];
@@ -591,7 +643,7 @@ __device__ __forceinline__ void march_step(StepCtx<S>& C, Lane<S>& L, int t, uns
     if constexpr (S::W20 == 2) {
       PC = add2(PC, add2(mk(f[0], f[1]), mk(f[4], f[5])));
     } else if constexpr (S::TIP2) {  // NaN > crit is false
-      PC = add2(PC, add2(mk(gtf(lo(SU), A.step_crit), gtf(hi(SU), A.step_crit)), mk(gtf(lo(SD), A.step_crit), gtf(hi(SD), A.step_crit))));
+      PC = add2(PC, add2(mk(gtf(lo(SU), A.step_cmp), gtf(hi(SU), A.step_cmp)), mk(gtf(lo(SD), A.step_cmp), gtf(hi(SD), A.step_cmp))));
     }
     L.sh[S0] = V0;
     ring_put<R_S3MX, S0>(C, L.s3mx, mk(smx[0], smx[1])); ring_put<R_S3C, S0>(C, L.s3c, mk(sc[0], sc[1]));
@@ -599,7 +651,7 @@ __device__ __forceinline__ void march_step(StepCtx<S>& C, Lane<S>& L, int t, uns
   }
   // ---- normals / slope / roughness of column jn = ce - 2 (ages: l = 2 - age) -------------------
   const int jn = ce - 2;
-  if (jn >= C.q0 && jn < C.q1) {
+  if (STRAIGHT || (jn >= C.q0 && jn < C.q1)) {
     const f2 ec = L.e[S2];
     f2 Sw = runA<S::WN0, S2, S0>(C, L), Sk = runB<S::WN0, S2, S0>(C, L), Sww = runQ<S::WN0, S2, S0>(C, L);
     f2 Sl = 0ull;
@@ -628,13 +680,17 @@ __device__ __forceinline__ void march_step(StepCtx<S>& C, Lane<S>& L, int t, uns
     L.dslope[S0] = n.slope;
     L.drough[S0] = n.rough;
     L.dflag[S0] = n.flag;
-    if constexpr (KN) store_normals(A.nx, A.ny, A.nz, C.out_ok, C.ocn, n.nx, n.ny, n.nz);
-    C.ocn += (size_t)A.rows;
+    if constexpr (KN)  // column jn is two columns ahead of the column the step layer is stored for
+      store_normals(A.nx, A.ny, A.nz, C.out_ok && (unsigned)(t - 6) < (unsigned)C.len, oc + 2u * (unsigned)A.rows, n.nx, n.ny, n.nz);
   }
-  if (t < 8) return;
+  if constexpr (!STRAIGHT) {
+    if (t < 8) return;
+  }
   // ---- stage C: step layer of column jo = ce - 4 and the fuse ----------------------------------
-  const int jo = ce - 4;
-  if (jo >= C.q1) return;
+  if constexpr (!STRAIGHT) {
+    if (ce - 4 >= C.q1) return;
+  }
+  const bool st_ok = C.out_ok && (unsigned)(t - 8) < (unsigned)C.len;  // column jo = ce - 4 = q0 + t - 8 belongs to the unit
   {
     float mx2[2];
     unsigned sflag = 0;
@@ -649,7 +705,7 @@ __device__ __forceinline__ void march_step(StepCtx<S>& C, Lane<S>& L, int t, uns
     f2 CNT = L.pcc[S2];
     if constexpr (S::W21 >= 0) CNT = add2(CNT, add2(ring_get<R_S3C, S1, S0>(C, L.s3c), ring_get<R_S3C, S3, S0>(C, L.s3c)));
     if constexpr (S::W22 == 0 || S::TIP2)
-      CNT = add2(CNT, add2(mk(gtf(lo(TL2), A.step_crit), gtf(hi(TL2), A.step_crit)), mk(gtf(lo(TR2), A.step_crit), gtf(hi(TR2), A.step_crit))));
+      CNT = add2(CNT, add2(mk(gtf(lo(TL2), A.step_cmp), gtf(hi(TL2), A.step_cmp)), mk(gtf(lo(TR2), A.step_cmp), gtf(hi(TR2), A.step_cmp))));
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
       auto R = [&](f2 x) { return r ? hi(x) : lo(x); };
@@ -664,22 +720,19 @@ __device__ __forceinline__ void march_step(StepCtx<S>& C, Lane<S>& L, int t, uns
     const f2 prod = mul2(mul2(CNT, A.k_inv_ncrit), stepMax);
     const f2 st = mk(fminf(lo(stepMax), lo(prod)), fminf(hi(stepMax), hi(prod)));
     // st < crit ? 1 - st/crit : 0 ; no finite step_height in the window (mx is NaN) -> layer stays NaN (StepFilter.cpp:169)
-    const f2 lin = fma2(st, A.k_minv_step, A.k_one);
-    const f2 outv = add2(mk(fmaxf(lo(lin), 0.0f), fmaxf(hi(lin), 0.0f)), sub2(MX, MX));  // mx NaN (or Inf - Inf) keeps the layer NaN
+    const f2 outv = add2(mk(fma_sat1(lo(st), A.minv_step_crit), fma_sat1(hi(st), A.minv_step_crit)), sub2(MX, MX));  // mx NaN (or Inf - Inf) keeps the layer NaN
     const f2 sl = L.dslope[S2], ro = L.drough[S2];
     const unsigned nf = L.dflag[S2];
     const f2 tr = mul2(A.k_fuse_w, add2(add2(sl, outv), ro));
-    if (C.out_ok) {
-      const size_t oc = C.oc;
+    if (st_ok) {
       *reinterpret_cast<f2*>(A.slope + oc) = sl;
       *reinterpret_cast<f2*>(A.rough + oc) = ro;
       *reinterpret_cast<f2*>(A.step + oc) = outv;
       *reinterpret_cast<f2*>(A.trav + oc) = tr;
     }
     // certified slow path: append flagged cells (bit 30: normals part, bit 31: step part)
-    const unsigned fl = C.out_ok ? (nf | (sflag << 2)) : 0u;  // bits 0/1: normals part of row x/y, bits 2/3: step part
-    if (__any_sync(FULL, fl != 0u)) append_flagged(A.count, A.list, A.cap, C.lane, (unsigned)C.oc, fl);
-    C.oc += (size_t)A.rows;
+    const unsigned fl = st_ok ? (nf | (sflag << 2)) : 0u;  // bits 0/1: normals part of row x/y, bits 2/3: step part
+    if (__any_sync(FULL, fl != 0u)) append_flagged(A.count, A.list, A.cap, C.lstate, C.lane, oc, fl);
   }
 }
 
@@ -703,9 +756,12 @@ __global__ void TE_KERNEL_ATTR k_chain_fused(const __grid_constant__ CUtensorMap
   const int nunits = A.lvl_unit0[NLVL];
   unsigned kglob = 0;  // chunks consumed so far by this warp (stage = kglob % NST, parity = (kglob / NST) & 1)
 
-  Lane<S> L;
+  Lane<S> L{};  // the warm-up steps of a unit read ring slots before they are written (results discarded)
   StepCtx<S> C{A, ering + lane * 8u, shbuf + lane * 8u, lane, 0, 0, 0, 0ull, 0ull, 0ull, 0ull,
-               reinterpret_cast<f2*>(smem_raw + warp * WARP_SMEM_BYTES + (NST * STAGE_BYTES + 2 * SHBUF_BYTES + 64)) + lane, false, 0, 0};
+               reinterpret_cast<f2*>(smem_raw + warp * WARP_SMEM_BYTES + (NST * STAGE_BYTES + 2 * SHBUF_BYTES + 64)) + lane,
+               bar0 + 8 * NST, false, 0u, 0};
+  if (lane == 0) asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(C.lstate), "r"(0u), "r"(LIST_CHUNK) : "memory");  // no chunk yet
+  __syncwarp();
 
   int unit = gwarp;  // the first unit is static, the rest come from the queue
   while (unit < nunits) {
@@ -725,8 +781,8 @@ __global__ void TE_KERNEL_ATTR k_chain_fused(const __grid_constant__ CUtensorMap
     const int nchunks = (nsteps + CH - 1) / CH;
     const int row0 = C.s0 + 2 * lane;
     C.out_ok = lane >= 1 && lane <= 30 && row0 < A.rows;
-    C.oc = (size_t)mapi * A.map_cells + (size_t)(C.q0 - A.out_col0) * A.rows + row0;
-    C.ocn = C.oc;
+    C.len = C.q1 - C.q0;
+    C.oc = (unsigned)mapi * A.map_cells + (unsigned)(C.q0 - A.out_col0 - 8) * (unsigned)A.rows + (unsigned)row0;
     if constexpr (S::MASKS) {
       const unsigned rm0 = (row0 >= 0 && row0 < A.rows) ? A.rowmask[row0] : 0u;
       const unsigned rm1 = (row0 + 1 >= 0 && row0 + 1 < A.rows) ? A.rowmask[row0 + 1] : 0u;
@@ -785,6 +841,7 @@ __global__ void TE_KERNEL_ATTR k_chain_fused(const __grid_constant__ CUtensorMap
     kglob += nchunks;
     unit = __shfl_sync(FULL, next, 0);
   }
+  finish_list(A.list, C.lstate, lane);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -913,6 +970,12 @@ int launch_shape(FusedState& st, const CUtensorMap& map, const FusedArgs& a, int
 
 }  // namespace
 
+size_t fused_list_capacity(size_t cells, int sms) {
+  // every flagged cell once, plus the padding of chunk tails (an append of up to 64 entries that does not fit opens a new
+  // chunk: at most 63 of LIST_CHUNK entries lost per chunk) and one open chunk per warp
+  return cells + cells / 7 + (size_t)sms * WARPS_PER_CTA * LIST_CHUNK + LIST_CHUNK;
+}
+
 void fused_plan(int rows, int out_ncols, int nmaps, int sms, int out[19]) {
   FusedArgs a{};
   a.nstrips = (rows + OROWS - 1) / OROWS;
@@ -937,7 +1000,7 @@ void FusedState::release() {
 }
 
 bool fused_eligible(FusedState& st, const std::vector<double>& X, const std::vector<double>& Y, const te_geometry* g,
-                    const te_chain_params* p) {
+                    const te_chain_params* p, cudaStream_t stream) {
   if (st.valid && std::memcmp(&st.key_geo, g, sizeof(*g)) == 0 && std::memcmp(&st.key_par, p, sizeof(*p)) == 0) return st.shape_id >= 0;
   st.valid = false;
   st.shape_id = -1;
@@ -961,7 +1024,9 @@ bool fused_eligible(FusedState& st, const std::vector<double>& X, const std::vec
   if (id < 0) return no("no fused instantiation for these window shapes");
   // on-circle tip membership, decided exactly like CircleIterator does (double, absolute positions)
   const double r1sq = p->step_first_radius * p->step_first_radius, r2sq = p->step_second_radius * p->step_second_radius;
-  std::vector<unsigned char> rm(g->rows, 0), cm(g->cols, 0);
+  std::vector<unsigned char>&rm = st.h_rowmask, &cm = st.h_colmask;  // owned by the state: the uploads below are asynchronous
+  rm.assign(g->rows, 0);
+  cm.assign(g->cols, 0);
   auto bits = [&](const std::vector<double>& P, int i, int n) {
     unsigned b = 0;
     if (i - 2 >= 0) {
@@ -978,17 +1043,23 @@ bool fused_eligible(FusedState& st, const std::vector<double>& X, const std::vec
   };
   for (int i = 0; i < g->rows; ++i) rm[i] = bits(X, i, g->rows);
   for (int j = 0; j < g->cols; ++j) cm[j] = bits(Y, j, g->cols);
+  // Kernels of an earlier asynchronous call may still read the tables: the overwrite is ordered after them on the context
+  // stream (a reallocation waits for the stream first).
   auto upload = [&](void*& d, size_t& cap, const std::vector<unsigned char>& h) {
     if (cap < h.size()) {
-      if (d) cudaFree(d);
+      if (d) {
+        if (cudaStreamSynchronize(stream) != cudaSuccess) return false;
+        cudaFree(d);
+      }
       d = nullptr;
       cap = 0;
       if (cudaMalloc(&d, h.size()) != cudaSuccess) return false;
       cap = h.size();
     }
-    return cudaMemcpy(d, h.data(), h.size(), cudaMemcpyHostToDevice) == cudaSuccess;
+    return cudaMemcpyAsync(d, h.data(), h.size(), cudaMemcpyHostToDevice, stream) == cudaSuccess;
   };
   if (!upload(st.d_rowmask, st.rowmask_cap, rm) || !upload(st.d_colmask, st.colmask_cap, cm)) return no("mask table upload failed");
+  if (cudaStreamSynchronize(stream) != cudaSuccess) return no("mask table upload failed");  // the host copies are reused
   st.shape_id = id;
   st.valid = true;
   st.why.clear();
@@ -1012,11 +1083,21 @@ void make_fixup_args(const FusedState& st, const SlabView& v, const ChainDev& p,
   *out = a;
 }
 
+const char* fused_launch_obstacle(const SlabView& v, int nmaps, const float* elev, const ChainOut& o) {
+  if ((reinterpret_cast<uintptr_t>(elev) & 15u) != 0) return "elevation pointer is not 16-byte aligned (TMA)";
+  if ((size_t)v.rows * v.out_ncols * (size_t)nmaps >= ((size_t)1 << 30)) return "launch covers 2^30 or more cells";
+  const float* outs[7] = {o.slope, o.step, o.rough, o.trav, o.nx, o.ny, o.nz};
+  for (const float* q : outs)
+    if (q && (reinterpret_cast<uintptr_t>(q) & 7u) != 0) return "an output layer is not 8-byte aligned";
+  const int have_n = (o.nx != nullptr) + (o.ny != nullptr) + (o.nz != nullptr);
+  if (have_n != 0 && have_n != 3) return "surface normal outputs must be given all three or none";
+  return nullptr;
+}
+
 int launch_chain_fused(FusedState& st, const SlabView& v, const ChainDev& p, int nmaps, const float* elev, const ChainOut& o,
                        unsigned* list, unsigned* count, unsigned cap, int sms, cudaStream_t s) {
   if (st.shape_id < 0) { st.why = "fused stencil not eligible"; return 1; }
-  if ((reinterpret_cast<uintptr_t>(elev) & 15u) != 0) { st.why = "elevation pointer is not 16-byte aligned"; return 1; }
-  if ((size_t)v.rows * v.out_ncols * (size_t)nmaps >= ((size_t)1 << 30)) { st.why = "launch covers 2^30 or more cells"; return 1; }
+  if (const char* why = fused_launch_obstacle(v, nmaps, elev, o)) { st.why = why; return 1; }
   PFN_encodeTiled enc = get_encode();
   if (!enc) { st.why = "cuTensorMapEncodeTiled entry point unavailable"; return 1; }
   CUtensorMap map;
@@ -1053,8 +1134,11 @@ int launch_chain_fused(FusedState& st, const SlabView& v, const ChainDev& p, int
   a.kp = (float)(-res / N);
   a.invN = (float)(1.0 / N);
   a.n_over_nm1 = (float)(N / (N - 1.0));
-  a.slope_crit = (float)p.slope_crit; a.inv_slope_crit = (float)(1.0 / p.slope_crit);
+  a.slope_crit = (float)p.slope_crit; a.inv_slope_crit = (float)(1.0 / p.slope_crit); a.minv_slope_crit = (float)(-1.0 / p.slope_crit);
+  a.minv_step_crit = -(float)(1.0 / p.step_crit); a.minv_rough_crit = (float)(-1.0 / p.rough_crit);
   a.step_crit = (float)p.step_crit; a.inv_step_crit = (float)(1.0 / p.step_crit);
+  a.step_cmp = (float)p.step_crit;
+  if ((double)a.step_cmp > p.step_crit) a.step_cmp = std::nextafterf(a.step_cmp, -INFINITY);
   a.inv_ncrit = (float)(1.0 / (double)p.ncrit);
   a.rough_crit = (float)p.rough_crit; a.inv_rough_crit = (float)(1.0 / p.rough_crit);
   a.fuse_w = p.fuse_w;

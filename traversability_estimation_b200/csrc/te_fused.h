@@ -14,6 +14,7 @@ struct FusedState {
   te_geometry key_geo{};
   te_chain_params key_par{};
   int shape_id = -1;
+  std::vector<unsigned char> h_rowmask, h_colmask;  // host copies of the tables below
   void* d_rowmask = nullptr;  // per-row on-circle membership bits
   void* d_colmask = nullptr;
   size_t rowmask_cap = 0, colmask_cap = 0;
@@ -25,7 +26,10 @@ struct FusedState {
 
 // True when the fused stencil has an instantiation for these window shapes (fills the tables).
 bool fused_eligible(FusedState& st, const std::vector<double>& X, const std::vector<double>& Y, const te_geometry* g,
-                    const te_chain_params* p);
+                    const te_chain_params* p, cudaStream_t stream);
+// Why this particular launch cannot use the fused stencil although the window shapes are eligible (pointer alignment, size,
+// partial normal outputs), or nullptr.  TE_KERNEL_AUTO runs the generic kernel instead.
+const char* fused_launch_obstacle(const SlabView& v, int nmaps, const float* elev, const ChainOut& o);
 
 // Arguments of the tier-2 fix-up kernel (te_fixup.cu): integer window description + parameters.
 struct FixupArgs {
@@ -45,7 +49,13 @@ struct FixupArgs {
 // Fills the tier-2 arguments for the shape the fused stencil was found eligible for.
 void make_fixup_args(const FusedState& st, const SlabView& v, const ChainDev& p, FixupArgs* out);
 void launch_fixup_t2(const FixupArgs& a, const float* elev, const ChainOut& o, const unsigned* list, const unsigned* count,
-                     unsigned cap, unsigned* list3, unsigned* count3, int sms, cudaStream_t s);
+                     unsigned cap, unsigned* list3, unsigned* count3, unsigned cap3, int sms, cudaStream_t s);
+
+// Work lists.  The fused kernel appends in warp-private chunks: entries equal to LIST_INVALID are padding and are skipped by the
+// consumers; count[0] = list entries reserved (chunks), count[1] = cells flagged, count[2] = overflow flag (never set when the
+// list holds fused_list_capacity() entries), count[4] = tier-3 entries, count[5] = tier-3 overflow flag.
+constexpr unsigned LIST_INVALID = 0xffffffffu;
+size_t fused_list_capacity(size_t cells, int sms);
 
 // Returns 0 on success.  Cells whose result could not be certified in fp32 are appended to `list`.
 // Work decomposition of the fused launch (see te_fused_plan in include/te_b200.h); host arithmetic only.

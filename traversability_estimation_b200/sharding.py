@@ -27,10 +27,16 @@ class SlabPlan:
 
 
 def plan_slab(cols_total: int, world: int, rank: int, halo: int) -> SlabPlan:
-    """Contiguous, near-equal column ranges; halos clipped at the map edges."""
+    """Contiguous, near-equal column ranges; halos clipped at the map edges.
+
+    Every rank must own at least `halo` columns: the exchange is one hop (a halo comes from the direct neighbour's owned
+    columns only), so narrower slabs would need data from two ranks away."""
     if not (0 <= rank < world) or cols_total < world:
         raise ValueError((cols_total, world, rank))
     base, extra = divmod(cols_total, world)
+    if world > 1 and base < halo:
+        raise ValueError(f"{cols_total} columns over {world} ranks leaves slabs of {base} columns, narrower than the "
+                         f"halo of {halo}: use fewer ranks (the halo exchange is one hop)")
     begin = rank * base + min(rank, extra)
     count = base + (1 if rank < extra else 0)
     hl = min(halo, begin)
