@@ -7,10 +7,12 @@
     python bench.py --impl reference ...      # the CPU restatement of the reference chain (oracle) on host cores
 
 A "step" is one pass of the hot path (elevation -> slope, step, roughness, traversability) over one
-map: at N=1 the 8192 x 8192 map the >=70 %-of-roofline target is quoted on; at N>1 the map grows with
-N (weak scaling): every rank owns an 8192-row x 8192-column slab of an 8192 x 8192*N map and exchanges
-its 4 boundary columns of `elevation` with its neighbours (NCCL send/recv over NVLink) inside the step.
-`--scaling strong` instead tiles the fixed 8192 x 8192 map (BASELINE config 3 verbatim).
+map: the 8192 x 8192 map of BASELINE config 3, the one the >=70 %-of-roofline target is quoted on.  At N>1
+the SAME map is tiled into N column slabs (strong scaling, config 3 verbatim): every rank owns 8192 rows x
+8192/N columns and pulls the 4 boundary columns of `elevation` of each neighbour into its halo inside
+the step — by default straight out of the neighbour's buffer over NVLink (CUDA IPC mapping, te_halo_pull
+of the C ABI; `--halo nccl` uses NCCL send/recv instead).  `--scaling weak` grows the map with N instead
+(every rank an 8192 x 8192 slab of an 8192 x 8192*N map).
 torch is plumbing only (device memory, streams, torch.distributed); every kernel timed here is ours,
 called through the C ABI of libte_b200.so.
 """
@@ -38,11 +40,12 @@ RES = 0.02
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=400)   # >= 0.2 s of timed device work at 8192^2
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="chain8192", choices=["chain8192", "chain2048", "batched512", "footprint4096", "slope8192"])
-    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--workload", default="chain8192", choices=["chain8192", "chain2048", "batched512", "footprint4096", "footprint4096_offset0", "slope8192", "plugin_chain"])
+    ap.add_argument("--scaling", default="strong", choices=["weak", "strong"])
+    ap.add_argument("--halo", default="ipc", choices=["ipc", "nccl"], help="halo exchange at N>1: peer-mapped pull (C ABI) or NCCL send/recv")
     ap.add_argument("--kernel", default="auto", choices=["auto", "generic", "fused"])
     ap.add_argument("--holes", type=float, default=0.01, help="fraction of NaN cells (blobs)")
     ap.add_argument("--rows", type=int, default=0)
@@ -135,6 +138,12 @@ class ClockSampler:
         for ln in self.proc.stdout:
             self.lines.append(ln.strip())
 
+    def wait_first(self, timeout=3.0):
+        """nvidia-smi needs a few hundred ms to deliver its first line: the timed region starts after it."""
+        t0 = time.perf_counter()
+        while self.proc and not self.lines and time.perf_counter() - t0 < timeout:
+            time.sleep(0.02)
+
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
@@ -161,6 +170,32 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def workload_name(rows, cols, holes):
+    """The same string in both arms (`--impl b200` and `--impl reference`): the driver compares them."""
+    return f"{rows}x{cols} elevation @ {RES} m, full filter chain (YAML parameters), {100 * holes:g} % NaN holes"
+
+
+def host_cpu():
+    """Model name and logical CPU count of the box (the CPU arms are only comparable on the same box)."""
+    model = None
+    try:
+        with open("/proc/cpuinfo") as f:
+            for ln in f:
+                if ln.lower().startswith("model name"):
+                    model = ln.split(":", 1)[1].strip()
+                    break
+    except OSError:
+        pass
+    return {"model": model, "logical_cpus": os.cpu_count(), "usable_threads": len(os.sched_getaffinity(0))}
+
+
+def bench_map_crop(n, holes):
+    """The top-left n x n crop of the 8192 x 8192 bench map (same generator and seed as the GPU arm, evaluated on the CPU)."""
+    import torch
+    z = terrain_torch(torch, 8192, 0, n, 8192, 3, holes, torch.device("cpu"))   # (n columns, 8192 rows)
+    return np.asfortranarray(z[:, :n].numpy().T)
+
+
 def measured_peak():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -185,31 +220,72 @@ def run_reference(args):
     if rank != 0:
         return
     from oracle import binding as ob
-    import synth
     n = 2048 if args.rows == 0 else args.rows
-    z = synth.terrain(n, n, RES, seed=3, preset="mixed", holes=args.holes)
+    z = bench_map_crop(n, args.holes)
     g = ob.Geometry.make(n, n, RES)
     p = ob.ChainParams.yaml_defaults(0)
     threads = len(os.sched_getaffinity(0))  # all host threads, also under torchrun (which exports OMP_NUM_THREADS=1)
-    for _ in range(args.warmup):
+    # each step is one pass over the bounded sample; the step count is capped so the whole run ends within minutes
+    steps, warmup = min(args.steps, 20), min(args.warmup, 2)
+    for _ in range(warmup):
         ob.chain(g, p, z, nthreads=threads)
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(steps):
         ob.chain(g, p, z, nthreads=threads)
     dt = time.perf_counter() - t0
-    val = n * n * args.steps / dt / 1e6
+    val = n * n * steps / dt / 1e6
+    args.steps, args.warmup = steps, warmup
     out = {"impl": "reference", "metric": "Mcells/s full filter chain, synthetic elevation", "value": val, "unit": "Mcells/s",
            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
            "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64 compute / f32 layers",
            "data": "synthetic",
-           "config": {"workload": "8192x8192 elevation @ 0.02 m, full fused chain (YAML parameters), 1 column slab(s) of 8192x8192",
-                      "sample": f"{n}x{n} crop per step (bounded sample of the workload)", "holes": args.holes},
+           "config": {"workload": workload_name(8192, 8192, args.holes),
+                      "sample": f"top-left {n}x{n} crop of the same map (same generator and seed as the GPU arm) per step",
+                      "holes": args.holes, "host": host_cpu()},
            "cpu_baseline": {"value": val, "unit": "Mcells/s", "cores": threads, "kind": "port",
                             "sample": f"{n}x{n} cells per step, {args.steps} steps, OpenMP over {threads} host threads; "
                                       "restated CPU chain (not the ROS/Eigen binary)"},
            "e2e": {"value": val, "unit": "Mcells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
     print(json.dumps(out))
+
+
+def run_plugin_chain(args, torch, dev):
+    """`--workload plugin_chain`: end to end through the reference-facing boundary itself — the C++ plugin shells
+    filters::{Slope,Step,Roughness}Filter<grid_map::GridMap>::update() driven like filters::FilterChain drives them under the
+    UNCHANGED YAML (robot_filter_parameter.yaml:10-28), host GridMaps in and out, `mapOut = mapIn` copies included.  Timed twice:
+    with the cross-plugin fusion registry (one te_chain launch per map) and with TE_B200_FUSE_CHAIN=0 (three stand-alone literal
+    kernels, the round-1 behaviour)."""
+    import tempfile
+    plugin = os.path.join(ROOT, "traversability_estimation_b200", "plugin")
+    subprocess.check_call(["make", "-C", plugin, "-s"])
+    rows = cols = args.rows or 4096
+    z = terrain_torch(torch, rows, 0, cols, cols, 3, args.holes, dev)
+    res = {}
+    with tempfile.TemporaryDirectory() as tmp:
+        src = os.path.join(tmp, "elev.bin")
+        z.cpu().numpy().tofile(src)
+        passes = max(2, min(args.steps, 5))
+        for name, fuse in (("fused_registry", "1"), ("standalone_literal", "0")):
+            env = dict(os.environ, TE_B200_FUSE_CHAIN=fuse)
+            r = subprocess.run([os.path.join(plugin, "test_plugins"), "bench", str(rows), str(cols), repr(RES), src, str(passes)],
+                               capture_output=True, text=True, env=env, timeout=1800)
+            if r.returncode != 0:
+                raise SystemExit("test_plugins bench failed: " + r.stdout[-500:] + r.stderr[-500:])
+            line = [ln for ln in r.stdout.splitlines() if ln.startswith("PLUGIN_CHAIN")][-1]
+            kv = dict(t.split("=") for t in line.split()[1:])
+            res[name] = {"mean_ms": float(kv["mean_ms"]), "best_ms": float(kv["best_ms"]), "fused_launches": int(kv["launches"]),
+                         "layers_from_cache": int(kv["served"]), "Mcells_per_s": rows * cols / (float(kv["mean_ms"]) * 1e-3) / 1e6}
+    ms = res["fused_registry"]["mean_ms"]
+    print(json.dumps({"metric": "Mcells/s full filter chain, synthetic elevation", "value": rows * cols / (ms * 1e-3) / 1e6,
+                      "unit": "Mcells/s", "n_gpus": 1, "steps": passes, "warmup": 1, "ms_per_step": ms, "higher_is_better": True,
+                      "scaling": "strong", "vs_baseline": None, "dtype": "f32 (f64 certified slow path)", "data": "synthetic",
+                      "config": {"workload": f"{rows}x{cols} elevation through the C++ plugin shells (slopeFilter, stepFilter, roughnessFilter "
+                                             "update() on host GridMaps, unchanged YAML)", "holes": args.holes},
+                      "roofline": None, "cpu_baseline": None,
+                      "e2e": {"value": rows * cols / (ms * 1e-3) / 1e6, "unit": "Mcells/s", "h2d_bytes_per_step": 4 * rows * cols,
+                              "d2h_bytes_per_step": 16 * rows * cols, "note": "wall clock around the three update() calls"},
+                      "plugin_chain": res, "gpu_launches": res["fused_registry"]["fused_launches"] * 3, "clocks": None}))
 
 
 def run_other(args, torch, dist, te, world, rank, local, dev):
@@ -250,9 +326,11 @@ def run_other(args, torch, dist, te, world, rank, local, dev):
         lay = [torch.empty((cols, rows), dtype=torch.float32, device=dev) for _ in range(4)]
         ctx.chain(g, prm, z, *lay, te.MEM_DEVICE)
         fp = te.FootprintParams.yaml_defaults()
+        if args.workload == "footprint4096_offset0":
+            fp.offset = 0.0   # SURVEY.md §8(d) config 5, the other variant: no annulus between radiusMin and radiusMax
         out = torch.empty((cols, rows), dtype=torch.float32, device=dev)
         cells = rows * cols
-        name = f"footprint sweep r=0.30 m offset=0.15 m over {rows}x{cols} traversability/slope/step/elevation"
+        name = f"footprint sweep r=0.30 m offset={fp.offset:.2f} m over {rows}x{cols} traversability/slope/step/elevation"
 
         def step():
             ctx.footprint(g, fp, lay[3], lay[0], lay[1], z, out, te.MEM_DEVICE)
@@ -314,7 +392,10 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     assert world == args.gpus or world == 1, (world, args.gpus)
 
-    if args.workload in ("batched512", "footprint4096", "slope8192"):
+    if args.workload == "plugin_chain":
+        assert world == 1
+        return run_plugin_chain(args, torch, dev)
+    if args.workload in ("batched512", "footprint4096", "footprint4096_offset0", "slope8192"):
         return run_other(args, torch, dist, te, world, rank, local, dev)
     rows = args.rows or {"chain8192": 8192, "chain2048": 2048}.get(args.workload, 8192)
     base_cols = args.cols or rows
@@ -348,11 +429,34 @@ def main():
     outs = outsets[0]
     rot = [0]
 
-    from traversability_estimation_b200.sharding import SlabPlan, exchange_halo
+    from traversability_estimation_b200.sharding import PeerHalo, SlabPlan, exchange_halo
     plan = SlabPlan(rank, world, cols_total, col0, my_cols, hl, hr)
+    # halo exchange inside the step: peer-mapped pull through the C ABI (default) or NCCL send/recv.  With rotated buffer sets
+    # (small slabs) each set has its own mapping.
+    peers = [PeerHalo(dist, ctx, te, e, plan) for e in elevs] if (world > 1 and args.halo == "ipc") else None
+    if peers:
+        torch.cuda.synchronize()
+        for ph in peers:
+            ph.publish()      # the owned columns are in place (the bench map is static)
+        ctx.synchronize()
+        dist.barrier()        # host-side ordering: every rank's ready event is recorded before anyone waits on it
+    hev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)] if world > 1 else []
+    timed = [False, 0]
 
     def exchange():
-        exchange_halo(dist, elevs[rot[0] % nsets], plan, H)
+        if world == 1:
+            return
+        k = rot[0] % nsets
+        rec = timed[0] and timed[1] < len(hev)
+        if rec:
+            hev[timed[1]][0].record(stream)
+        if peers:
+            peers[k].pull(g)
+        else:
+            exchange_halo(dist, elevs[k], plan, H)
+        if rec:
+            hev[timed[1]][1].record(stream)
+            timed[1] += 1
 
     def step():
         exchange()
@@ -368,29 +472,34 @@ def main():
 
     sampler = ClockSampler(local)
     if rank == 0:
-        sampler.start()  # nvidia-smi needs ~100 ms to deliver its first line: start ahead of the warm-up passes
+        sampler.start()
     for _ in range(max(args.warmup, 3)):
         step()
     barrier()
+    if rank == 0:
+        sampler.wait_first()  # the timed region starts only once nvidia-smi delivers samples
     ctx.timing()  # drop anything accumulated
     ctx.enable_timing(True)
     launches0, _ = ctx.stats()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    timed[0] = True
     ev0.record(stream)
     for _ in range(args.steps):
         step()
     ev1.record(stream)
     barrier()
+    timed[0] = False
     ms_total = ev0.elapsed_time(ev1)
+    halo_ms = (sum(a.elapsed_time(b) for a, b in hev[:timed[1]]) / max(timed[1], 1)) if world > 1 else 0.0
     clocks = sampler.stop() if rank == 0 else None
     main_ms, fix_ms, nlaunch = ctx.timing()
     ctx.enable_timing(False)
     launches1, slow_cells = ctx.stats()
-    t = torch.tensor([ms_total, main_ms / max(nlaunch, 1), fix_ms / max(nlaunch, 1)], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms_total, main_ms / max(nlaunch, 1), fix_ms / max(nlaunch, 1), halo_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total, main_avg, fix_avg = (float(v) for v in t.tolist())
+    ms_total, main_avg, fix_avg, halo_ms = (float(v) for v in t.tolist())
     cells_total = rows * cols_total
     value = cells_total * args.steps / (ms_total * 1e-3) / 1e6
 
@@ -422,7 +531,7 @@ def main():
             dist.destroy_process_group()
         return
 
-    # ---- CPU baseline: the oracle (restated reference chain) on a bounded crop, host threads
+    # ---- CPU baseline: the oracle (restated reference chain) on a bounded crop of the same map, host threads
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         from oracle import binding as ob
@@ -435,9 +544,17 @@ def main():
         t0 = time.perf_counter()
         ob.chain(og, op, crop, nthreads=threads)
         dt = time.perf_counter() - t0
+        n1 = min(512, n)   # the reference is single-threaded per filter; one thread on a smaller crop
+        c1 = np.asfortranarray(crop[:n1, :n1])
+        t0 = time.perf_counter()
+        ob.chain(ob.Geometry.make(n1, n1, RES), op, c1, nthreads=1)
+        dt1 = time.perf_counter() - t0
         cpu = {"value": n * n / dt / 1e6, "unit": "Mcells/s", "cores": threads, "kind": "port",
                "sample": f"{n}x{n} crop of the same map, one pass, OpenMP over {threads} host threads "
-                         f"({dt:.2f} s); restated CPU chain, not the ROS/Eigen binary"}
+                         f"({dt:.2f} s); restated CPU chain, not the ROS/Eigen binary",
+               "single_thread": {"value": n1 * n1 / dt1 / 1e6, "unit": "Mcells/s", "cores": 1,
+                                 "sample": f"{n1}x{n1} crop of the same map, one pass, one thread ({dt1:.2f} s)"},
+               "host": host_cpu()}
 
     peak, peak_src = measured_peak()
     cells_per_launch = rows * my_cols
@@ -450,8 +567,10 @@ def main():
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps,
         "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32 (f64 certified slow path)",
         "data": "synthetic",
-        "config": {"workload": f"{rows}x{cols_total} elevation @ {RES} m, full fused chain (YAML parameters), "
-                               f"{world} column slab(s) of {rows}x{my_cols}" + (" + 4-column NCCL halo exchange" if world > 1 else ""),
+        "config": {"workload": workload_name(rows, cols_total, args.holes),
+                   "tiling": f"{world} column slab(s) of {rows}x{my_cols}" +
+                             ((" + 4-column halo, " + ("peer-mapped pull over NVLink (te_halo_pull, CUDA IPC)" if args.halo == "ipc" else "NCCL send/recv"))
+                              if world > 1 else ""),
                    "holes": args.holes, "kernel": args.kernel,
                    "l2": ("working set %.2f GB/GPU per pass > 126 MB L2, no flush needed" % (pass_bytes / 1e9)) if nsets == 1 else
                          ("%d buffer sets rotated (%.0f MB total) so every pass streams from HBM" % (nsets, nsets * pass_bytes / 1e6)),
@@ -461,7 +580,12 @@ def main():
                      "traffic": traffic, "peak_source": peak_src,
                      "kernel": "k_chain_fused" if args.kernel != "generic" else "k_chain_generic",
                      "kernel_ms": main_avg, "fixup_kernel_ms": fix_avg,
-                     "algorithmic_bytes_per_launch": ALG_BYTES_PER_CELL * cells_per_launch},
+                     "algorithmic_bytes_per_launch": ALG_BYTES_PER_CELL * cells_per_launch,
+                     # the four layers are final only after the fix-up tiers: the whole device step against the same peak
+                     "step": {"ms": ms_total / args.steps, "achieved": ALG_BYTES_PER_CELL * cells_per_launch / (ms_total / args.steps * 1e-3) / 1e9,
+                              "frac": ALG_BYTES_PER_CELL * cells_per_launch / (ms_total / args.steps * 1e-3) / 1e9 / peak}},
+        "halo_ms": halo_ms if world > 1 else None,
+        "halo": (args.halo if world > 1 else None),
         "cpu_baseline": cpu,
         "e2e": e2e,
         "gpu_launches": int(launches1 - launches0),

@@ -32,7 +32,7 @@ typedef enum te_status {
   TE_ERR_MISSING_LAYER = -2, /* a required input layer pointer is null (reference: GridMap::at throws) */
   TE_ERR_CUDA = -3,          /* CUDA runtime/driver failure, or no device */
   TE_ERR_UNSUPPORTED = -4,   /* e.g. non-zero circular-buffer start index */
-  TE_ERR_NCCL = -5
+  TE_ERR_NCCL = -5           /* reserved (the halo exchange of this library is peer-mapped, see te_halo_pull) */
 } te_status;
 
 /* Where the layer pointers passed to a call live. */
@@ -86,7 +86,9 @@ typedef struct te_footprint_params {
   double max_gap_width;           /* maxGapWidth_ (robot.yaml:10) */
   double critical_step_height;    /* criticalStepHeight_ (TraversabilityMap.cpp:117-126) */
   int32_t radius_is_integer_norm; /* SpiralIterator::getCurrentRadius via Eigen integer norm (1) or exact (0) */
-  int32_t reserved0;
+  int32_t verify_roughness;       /* checkForRoughness_ (robot_footprint_parameter.yaml:9 `verify_roughness_footprint`):
+                                     isTraversableForFilters also runs checkForRoughness (TraversabilityMap.cpp:779-783, 895-921);
+                                     needs the traversability_roughness layer, i.e. te_footprint2 */
 } te_footprint_params;
 
 /* Which implementation te_chain uses. AUTO picks the fused stencil when the window shapes have a
@@ -101,6 +103,11 @@ int te_create(te_ctx** out, int device);
 int te_destroy(te_ctx* ctx);
 const char* te_last_error(void);
 int te_abi_version(void);
+
+/* Page-locked host memory for layers handed to TE_MEM_HOST calls (cudaHostAlloc): pageable layers work too, but their
+ * transfers are staged by the driver at roughly half the PCIe rate.  The plugin shells keep their cached layers here. */
+int te_host_alloc(void** out, size_t bytes);
+int te_host_free(void* p);
 
 /* Run subsequent calls on an external stream (cudaStream_t passed as void*; NULL restores the
  * context's own stream).  Device-memory calls are asynchronous on that stream; te_synchronize waits. */
@@ -120,6 +127,11 @@ int te_get_timing(te_ctx* ctx, double* main_ms, double* fixup_ms, int64_t* sampl
  * [2] non-zero if a work list overflowed (cannot happen: the lists are sized for every cell of the launch);
  * [4] cells tier 2 passed on to the literal kernel (tier 3); [3] reserved (0). */
 int te_get_flag_counters(te_ctx* ctx, uint32_t out[5]);
+/* Why tier 2 passed cells of the last fused launch on to the literal kernel: reasons[r] = cells escalated for reason r
+ * (1 degenerate / 2 rank-deficient / 3 small eigen-gap full window, 4 no convergence / 5 rank / 6 conditioning of a partial
+ * window, 7 null eigenvector, 8 n_z == 0, 9 n_z on a float32 rounding boundary); valid_cells[n] = escalated cells whose
+ * normals window held n valid cells.  Diagnostics only; no reference counterpart. */
+int te_get_escalation_stats(te_ctx* ctx, uint32_t reasons[16], uint32_t valid_cells[26]);
 /* Work decomposition the fused kernel uses for `nmaps` maps of rows x out_ncols output cells on a GPU with `sms`
  * multiprocessors (host arithmetic only, needs no GPU; no reference counterpart — the reference iterates cell by cell).
  * Units are (level, map, column segment, 60-row strip), popped from a queue in that order; a level is a run of columns cut
@@ -167,10 +179,54 @@ int te_footprint(te_ctx* ctx, const te_geometry* g, const te_slab* slab, const t
                  float* traversability_footprint, float* slope_footprint_or_null, float* step_footprint_or_null,
                  int memory);
 
-/* CUDA IPC helpers so that a neighbour rank's slab can be read in place over NVLink. */
-int te_ipc_export(const void* device_ptr, void* handle_64_bytes);
-int te_ipc_open(const void* handle_64_bytes, void** device_ptr_out);
+/* te_footprint with the traversability_roughness layer: when p->verify_roughness is set, a visited cell is also blocked by
+ * checkForRoughness (TraversabilityMap.cpp:895-921: more than floor(1.5 * 3 res * max_gap_width / 3 / res^2) cells of zero
+ * roughness traversability within 3 res).  `roughness` may be NULL when the flag is clear; roughness_footprint receives the
+ * memoisation layer the reference keeps (optional). */
+int te_footprint2(te_ctx* ctx, const te_geometry* g, const te_slab* slab, const te_footprint_params* p,
+                  const float* traversability, const float* slope, const float* step, const float* roughness_or_null,
+                  const float* elevation, float* traversability_footprint, float* slope_footprint_or_null,
+                  float* step_footprint_or_null, float* roughness_footprint_or_null, int memory);
+
+/* ---- Multi-GPU: one map tiled into column slabs, one process (rank) per GPU -------------------------------
+ * The chain and the footprint sweep are stencils of fixed radius, so the only exchange step is a one-shot copy of the
+ * neighbours' boundary columns of the INPUT layer(s) into this rank's halo.  The reference has no counterpart (it is a
+ * single-process CPU node; TraversabilityMap.cpp:202-237 runs the chain on one whole map); these entry points are what a
+ * sharded caller of te_chain / te_footprint needs around the `te_slab` argument:
+ *   1. every rank exports its slab buffer (te_ipc_export) and a "layer ready" event (te_event_create_ipc), ships the two
+ *      handles (TE_IPC_HANDLE_BYTES and 64 bytes) to its neighbours over any channel (MPI, a socket, torch.distributed), and opens theirs
+ *      (te_ipc_open / te_event_open_ipc) — once;
+ *   2. per map: te_event_record(ready) after the rank's producer wrote its owned columns; te_halo_pull() then waits for the
+ *      neighbours' ready events on the context stream and copies their boundary columns straight out of their buffers over
+ *      NVLink (peer-mapped cudaMemcpyAsync, no staging, no collective); te_chain(..., slab, ..., TE_MEM_DEVICE) follows on the
+ *      same stream.  Outputs stay sharded.
+ * A cross-process event wait sees the most recent te_event_record that the RECORDING process had issued when the waiting
+ * process called te_halo_pull; callers that rewrite a layer per frame order the two host-side (a message after the record)
+ * and must not overwrite boundary columns a neighbour may still be pulling (double-buffer, or wait for the neighbour's own
+ * event recorded after its pull). */
+#define TE_IPC_HANDLE_BYTES 80 /* CUDA IPC handle of the containing allocation + offset of the pointer inside it */
+int te_ipc_export(const void* device_ptr, void* handle_TE_IPC_HANDLE_BYTES);
+int te_ipc_open(const void* handle_TE_IPC_HANDLE_BYTES, void** device_ptr_out);
 int te_ipc_close(void* device_ptr);
+/* Interprocess events (cudaEventInterprocess | cudaEventDisableTiming). */
+int te_event_create_ipc(te_ctx* ctx, void** event_out, void* handle_64_bytes_out);
+int te_event_open_ipc(const void* handle_64_bytes, void** event_out);
+int te_event_record(te_ctx* ctx, void* event);   /* on the context stream */
+int te_event_destroy(void* event);
+
+/* A neighbour's slab buffer as mapped into this process: `layer` holds the global columns
+ * [slab.col_begin - slab.halo_left, slab.col_begin + slab.col_count + slab.halo_right) of a rows x cols layer. */
+typedef struct te_halo_peer {
+  const float* layer;   /* te_ipc_open()ed pointer (or a plain device pointer of a peer-accessible GPU in this process) */
+  te_slab slab;         /* the neighbour's slab */
+  void* ready_event;    /* te_event_open_ipc()ed event, or NULL: no wait */
+} te_halo_peer;
+
+/* Fill this rank's halo columns of `layer` (a buffer laid out like the te_chain input for `slab`) from the neighbours' OWNED
+ * columns, asynchronously on the context stream.  The exchange is one hop: TE_ERR_BAD_ARG if a neighbour owns fewer columns
+ * than the halo needs.  Pass NULL for a side without a neighbour (map edge). */
+int te_halo_pull(te_ctx* ctx, const te_geometry* g, const te_slab* slab, float* layer,
+                 const te_halo_peer* left_or_null, const te_halo_peer* right_or_null);
 
 #ifdef __cplusplus
 }

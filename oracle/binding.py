@@ -43,7 +43,7 @@ class ChainParams(C.Structure):
 class FootprintParams(C.Structure):
     _fields_ = [("radius", C.c_double), ("offset", C.c_double), ("traversability_default", C.c_double),
                 ("max_gap_width", C.c_double), ("critical_step_height", C.c_double),
-                ("radius_is_integer_norm", C.c_int32), ("reserved0", C.c_int32)]
+                ("radius_is_integer_norm", C.c_int32), ("verify_roughness", C.c_int32)]
 
     @classmethod
     def yaml_defaults(cls):
@@ -75,6 +75,7 @@ def lib():
         L.teo_fuse.argtypes = [C.c_int64, C.c_float, fp, fp, fp, fp]
         L.teo_chain.argtypes = [G, P, fp, fp, fp, fp, fp, fp, fp, fp, C.c_int]
         L.teo_footprint.argtypes = [G, F, fp, fp, fp, fp, fp, fp, fp, C.c_int]
+        L.teo_footprint2.argtypes = [G, F, fp, fp, fp, fp, fp, fp, fp, fp, fp, C.c_int]
         L.teo_spiral_offsets.argtypes = [C.c_double, C.c_double, ip, ip, C.c_int]
         L.teo_circle_cells.argtypes = [G, C.c_int, C.c_int, C.c_double, ip, ip, C.c_int]
         L.teo_max_threads.restype = C.c_int
@@ -145,12 +146,18 @@ def chain(g, p, elevation, nthreads=0, with_normals=False):
     return o
 
 
-def footprint(g, fp, traversability, slope_l, step_l, elevation, nthreads=0):
+def footprint(g, fp, traversability, slope_l, step_l, elevation, nthreads=0, roughness=None):
+    """Returns (traversability_footprint, slope_footprint, step_footprint[, roughness_footprint when `roughness` is given])."""
     t, s, st, e = (_layer(g, v) for v in (traversability, slope_l, step_l, elevation))
     out, sfp, stfp = _new(g), _new(g), _new(g)
-    rc = lib().teo_footprint(C.byref(g), C.byref(fp), _f(t), _f(s), _f(st), _f(e), _f(out), _f(sfp), _f(stfp), nthreads)
+    if roughness is None:
+        rc = lib().teo_footprint(C.byref(g), C.byref(fp), _f(t), _f(s), _f(st), _f(e), _f(out), _f(sfp), _f(stfp), nthreads)
+        assert rc == 0, rc
+        return out, sfp, stfp
+    r, rfp = _layer(g, roughness), _new(g)
+    rc = lib().teo_footprint2(C.byref(g), C.byref(fp), _f(t), _f(s), _f(st), _f(r), _f(e), _f(out), _f(sfp), _f(stfp), _f(rfp), nthreads)
     assert rc == 0, rc
-    return out, sfp, stfp
+    return out, sfp, stfp, rfp
 
 
 def spiral_offsets(radius, resolution):

@@ -63,7 +63,7 @@ typedef struct teo_footprint_params {
   double max_gap_width;           /* maxGapWidth_, robot.yaml:10 */
   double critical_step_height;    /* criticalStepHeight_ = stepFilter critical_value, TraversabilityMap.cpp:117-126 */
   int32_t radius_is_integer_norm; /* 1: SpiralIterator::getCurrentRadius uses Eigen's integer norm (floor), 0: exact */
-  int32_t reserved0;
+  int32_t verify_roughness;       /* checkForRoughness_ (robot_footprint_parameter.yaml:9 verify_roughness_footprint) */
 } teo_footprint_params;
 
 /* All layers: float32, column-major, value(i,j) = data[j*rows + i]; NaN/Inf = invalid cell.
@@ -87,6 +87,12 @@ int teo_chain(const teo_geometry* g, const teo_chain_params* p, const float* ele
 int teo_footprint(const teo_geometry* g, const teo_footprint_params* p, const float* traversability,
                   const float* slope, const float* step, const float* elevation,
                   float* out_footprint, float* slope_fp_or_null, float* step_fp_or_null, int nthreads);
+
+/* The same with checkForRoughness (TraversabilityMap.cpp:779-783, 895-921) when p->verify_roughness is set: `roughness` is the
+ * traversability_roughness layer, rough_fp receives the roughness_footprint memoisation layer (may be NULL). */
+int teo_footprint2(const teo_geometry* g, const teo_footprint_params* p, const float* traversability,
+                   const float* slope, const float* step, const float* roughness_or_null, const float* elevation,
+                   float* out_footprint, float* slope_fp_or_null, float* step_fp_or_null, float* rough_fp_or_null, int nthreads);
 
 /* Visit order of grid_map::SpiralIterator for a centre far from the map border: writes up to `cap`
  * (di,dj) pairs, returns the number of cells visited.  radius/resolution in metres. */

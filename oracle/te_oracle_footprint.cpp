@@ -4,7 +4,7 @@
  * Restates TraversabilityMap::traversabilityFootprint(radius, offset)
  *   traversability_estimation/src/TraversabilityMap.cpp:307-318
  * and everything it reaches: isTraversable(center, radiusMax, ..., radiusMin) :654-746,
- * isTraversableForFilters :774-792, checkForStep :794-865, checkForSlope :867-893, together with the
+ * isTraversableForFilters :774-792, checkForStep :794-865, checkForSlope :867-893, checkForRoughness :895-921, together with the
  * grid_map_core pieces those lines call (SpiralIterator, CircleIterator, LineIterator, getSubmap,
  * getIndex, isInside — SURVEY.md Appendix A.1-A.3, recalled from ros-noetic-grid-map 1.6.x).
  *
@@ -110,6 +110,21 @@ bool check_slope(const Map& m, const teo_footprint_params& p, int i, int j) {
   for_circle(m, i, j, windowRadius, [&](int a, int b) {
     if (m.at(m.slope, a, b) == 0.0) ++nSlopes;                                        // :881
     if (nSlopes > nSlopesCritical) ok = false;                                        // :882-885
+  });
+  return ok;
+}
+
+// TraversabilityMap::checkForRoughness, TraversabilityMap.cpp:895-921 (memoisation removed: pure function of the layer).
+bool check_roughness(const Map& m, const teo_footprint_params& p, const float* rough, int i, int j) {
+  if (!((double)rough[(size_t)j * m.rows + i] == 0.0)) return true;                   // :897
+  const double windowRadius = 3.0 * m.res;                                            // :899
+  const double criticalLength = p.max_gap_width / 3.0;                                // :900
+  const int nRoughnessCritical = (int)std::floor(1.5 * windowRadius * criticalLength / std::pow(m.res, 2));  // :901
+  int nRoughness = 0;
+  bool ok = true;
+  for_circle(m, i, j, windowRadius, [&](int a, int b) {
+    if ((double)rough[(size_t)b * m.rows + a] == 0.0) ++nRoughness;                   // :909
+    if (nRoughness > nRoughnessCritical) ok = false;                                  // :910-913
   });
   return ok;
 }
@@ -251,7 +266,13 @@ int teo_spiral_offsets(double radius, double resolution, int32_t* di, int32_t* d
 
 int teo_footprint(const teo_geometry* g, const teo_footprint_params* p, const float* trav, const float* slope, const float* step,
                   const float* elev, float* out, float* slope_fp, float* step_fp, int nthreads) {
+  return teo_footprint2(g, p, trav, slope, step, nullptr, elev, out, slope_fp, step_fp, nullptr, nthreads);
+}
+
+int teo_footprint2(const teo_geometry* g, const teo_footprint_params* p, const float* trav, const float* slope, const float* step,
+                   const float* rough, const float* elev, float* out, float* slope_fp, float* step_fp, float* rough_fp, int nthreads) {
   if (!g || g->rows <= 0 || g->cols <= 0 || !(g->resolution > 0.0) || !p || !trav || !slope || !step || !elev || !out) return 1;
+  if (p->verify_roughness && !rough) return 1;
   Map m{g->rows, g->cols, g->resolution, {g->length_x, g->length_y}, {g->position_x, g->position_y}, trav, slope, step, elev, {}, {}};
   m.X.resize(m.rows);
   m.Y.resize(m.cols);
@@ -279,7 +300,13 @@ int teo_footprint(const teo_geometry* g, const teo_footprint_params* p, const fl
         t_ok = check_step(m, *p, i, j);
         if (step_fp && m.at(m.step, i, j) == 0.0) step_fp[c] = t_ok ? 1.0f : 0.0f;     // :859,:842,:854
       }
-      blocked[c] = !(s_ok && t_ok);
+      bool r_ok = true;
+      if (rough_fp) rough_fp[c] = kNaNf;
+      if (s_ok && t_ok && p->verify_roughness) {                                       // :779-783: only after slope and step passed
+        r_ok = check_roughness(m, *p, rough, i, j);
+        if (rough_fp && (double)rough[c] == 0.0) rough_fp[c] = r_ok ? 1.0f : 0.0f;     // :915,:911
+      }
+      blocked[c] = !(s_ok && t_ok && r_ok);
     }
 
   const double radiusMin = p->radius;                         // :313  isTraversable(center, radius + offset, traversability, radius)

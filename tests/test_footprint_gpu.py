@@ -104,3 +104,53 @@ def test_footprint_slabs_equal_whole_map(te, ctx, oracle):
     with pytest.raises(te.TEError):
         ctx.footprint(g, fp, *[x[130:300].contiguous() for x in lay], torch.empty((160, rows), dtype=torch.float32, device="cuda"),
                       te.MEM_DEVICE, slab=te.Slab(140, 160, 10, 0))
+
+
+@pytest.mark.parametrize("offset", [0.15, 0.0])
+def test_footprint_1024_matches_oracle(te, ctx, oracle, offset):
+    """the sweep at 1024 x 1024 on chain outputs, both offsets of BASELINE config 5."""
+    n = 1024
+    z = synth.terrain(n, n, 0.02, 1024, "mixed")
+    og, g = oracle.Geometry.make(n, n, 0.02), te.Geometry.make(n, n, 0.02)
+    ch = oracle.chain(og, oracle.ChainParams.yaml_defaults(0), z)
+    fo, ft = oracle.FootprintParams.yaml_defaults(), te.FootprintParams.yaml_defaults()
+    fo.offset = ft.offset = offset
+    t, s, st, e = (np.asfortranarray(x, dtype=np.float32) for x in (ch["traversability"], ch["slope"], ch["step"], z))
+    ref, rs, rt = oracle.footprint(og, fo, t, s, st, e)
+    out, sfp, tfp = np.empty_like(t), np.empty_like(t), np.empty_like(t)
+    ctx.footprint(g, ft, t, s, st, e, out, te.MEM_HOST, slope_fp=sfp, step_fp=tfp)
+    assert _close(out, ref), (int((out != ref).sum()), float(np.nanmax(np.abs(out - ref))))
+    assert _same(sfp, rs) and _same(tfp, rt)
+    assert (ref == 0).any() and (ref > 0).any()
+
+
+def test_footprint_with_roughness_verification(te, ctx, oracle):
+    """verify_roughness_footprint (robot_footprint_parameter.yaml:9): isTraversableForFilters also runs checkForRoughness
+    (TraversabilityMap.cpp:779-783, 895-921).  A rough terrain makes zero-roughness-traversability patches that block cells the
+    slope/step checks let through."""
+    rows, cols = 200, 180
+    z = synth.terrain(rows, cols, 0.02, 61, "rough")
+    z[60:110, 40:100] = synth.terrain(50, 60, 0.02, 62, "gentle")     # a smooth island in rough ground
+    og, g = oracle.Geometry.make(rows, cols, 0.02), te.Geometry.make(rows, cols, 0.02)
+    ch = oracle.chain(og, oracle.ChainParams.yaml_defaults(0), z)
+    assert (ch["roughness"] == 0).sum() > 500
+    fo, ft = oracle.FootprintParams.yaml_defaults(), te.FootprintParams.yaml_defaults()
+    t, s, st, r, e = (np.asfortranarray(x, dtype=np.float32) for x in (ch["traversability"], ch["slope"], ch["step"], ch["roughness"], z))
+    base, _, _ = oracle.footprint(og, fo, t, s, st, e)
+    fo.verify_roughness = ft.verify_roughness = 1
+    ref, rs, rt, rr = oracle.footprint(og, fo, t, s, st, e, roughness=r)
+    assert (np.nan_to_num(ref) != np.nan_to_num(base)).sum() > 100       # the extra check changes the layer
+    assert np.isfinite(rr).sum() > 0 and (rr == 0).sum() > 0
+    import os
+    for brute in (True, False):
+        if brute:
+            os.environ["TE_FOOTPRINT_BRUTE"] = "1"
+        else:
+            os.environ.pop("TE_FOOTPRINT_BRUTE", None)
+        out, sfp, tfp, rfp = (np.empty_like(t) for _ in range(4))
+        ctx.footprint(g, ft, t, s, st, e, out, te.MEM_HOST, slope_fp=sfp, step_fp=tfp, roughness=r, roughness_fp=rfp)
+        assert (_same if brute else _close)(out, ref)
+        assert _same(sfp, rs) and _same(tfp, rt) and _same(rfp, rr)
+    with pytest.raises(te.TEError) as err:   # the flag without the layer: TE_ERR_MISSING_LAYER, like GridMap::at on a missing layer
+        ctx.footprint(g, ft, t, s, st, e, out, te.MEM_HOST)
+    assert err.value.code == -2

@@ -55,3 +55,23 @@ def test_check_for_slope_threshold(oracle):
     import math
     assert math.floor(2 * (3 * 0.02) * (0.3 / 3.0) / 0.02 ** 2) == 29
     assert math.floor(2 * (3 * 0.03) * (0.3 / 3.0) / 0.03 ** 2) == 20
+
+
+def test_check_for_roughness_blocks_rough_patches(oracle):
+    """checkForRoughness (TraversabilityMap.cpp:895-921): a cell of zero roughness-traversability is blocked when more than
+    floor(1.5 * 3 res * (max_gap_width / 3) / res^2) = 22 cells of its 3 res circle (29 cells) are zero too."""
+    rows, cols = 40, 40
+    g = oracle.Geometry.make(rows, cols, 0.02)
+    one = np.ones((rows, cols), np.float32, order="F")
+    z = np.zeros((rows, cols), np.float32, order="F")
+    rough = one.copy()
+    rough[10:30, 10:30] = 0.0                       # a 20 x 20 patch of zero roughness traversability
+    fp = oracle.FootprintParams.yaml_defaults()
+    fp.radius, fp.offset = 0.0, 0.0                 # the sweep degenerates to the centre cell: blocked -> 0, else its traversability
+    base, _, _ = oracle.footprint(g, fp, one, one, one, z)
+    assert (base == 1.0).all()
+    fp.verify_roughness = 1
+    out, _, _, rfp = oracle.footprint(g, fp, one, one, one, z, roughness=rough)
+    assert out[20, 20] == 0.0 and rfp[20, 20] == 0.0          # deep inside the patch: 29 zero cells > 22
+    assert out[10, 10] == 1.0 and rfp[10, 10] == 1.0          # the patch corner sees only ~11 zero cells
+    assert out[5, 5] == 1.0 and np.isnan(rfp[5, 5])           # not a zero-roughness cell: the check is skipped (:897)

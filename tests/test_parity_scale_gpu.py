@@ -140,11 +140,10 @@ def test_auto_falls_back_when_a_pointer_is_misaligned(te, ctx):
     rows, cols = 256, 192
     zh = synth.terrain(rows, cols, 0.02, 5, "mixed")
     g, p = te.Geometry.make(rows, cols, 0.02), te.ChainParams.yaml_defaults(0)
-    flat = torch.empty(rows * cols + 4, dtype=torch.float32, device="cuda")
-    z_al = flat[:rows * cols]
-    z_al.copy_(torch.from_numpy(np.ascontiguousarray(zh.T)).reshape(-1))
-    z_mis = flat[1:rows * cols + 1]          # 4-byte offset
-    z_mis.copy_(z_al.clone())
+    z_al = torch.from_numpy(np.ascontiguousarray(zh.T)).reshape(-1).cuda()
+    z_mis = torch.empty(rows * cols + 4, dtype=torch.float32, device="cuda")[1:rows * cols + 1]   # 4-byte offset
+    z_mis.copy_(z_al)
+    torch.cuda.synchronize()   # the context runs on its own stream
     new = lambda: torch.empty(rows * cols + 4, dtype=torch.float32, device="cuda")  # noqa: E731
     ctx.set_kernel(te.KERNEL_AUTO)
     base = [new()[:rows * cols] for _ in range(4)]
@@ -156,7 +155,8 @@ def test_auto_falls_back_when_a_pointer_is_misaligned(te, ctx):
     for a, b in zip(base, mis):
         ok = ~torch.isnan(a)
         assert torch.equal(torch.isnan(a), torch.isnan(b))
-        assert float((a[ok].double() - b[ok].double()).abs().max()) < 2e-6   # fused vs literal
+        d = (a[ok].double() - b[ok].double()).abs()
+        assert bool((d <= 1e-5 * b[ok].double().abs() + 1e-6).all())       # fused stencil vs literal kernel
     ctx.set_kernel(te.KERNEL_FUSED)
     with pytest.raises(te.TEError) as e:
         ctx.chain(g, p, z_mis, *mis, te.MEM_DEVICE)

@@ -16,8 +16,12 @@ MEM_HOST, MEM_DEVICE = 0, 1
 KERNEL_AUTO, KERNEL_GENERIC, KERNEL_FUSED = 0, 1, 2
 
 EXPORTS = ["te_create", "te_destroy", "te_last_error", "te_abi_version", "te_set_stream", "te_synchronize",
-           "te_set_kernel", "te_get_stats", "te_enable_timing", "te_get_timing", "te_get_flag_counters", "te_fused_plan", "te_slope", "te_normals", "te_step", "te_roughness", "te_chain",
-           "te_chain_batched", "te_footprint", "te_ipc_export", "te_ipc_open", "te_ipc_close"]
+           "te_set_kernel", "te_get_stats", "te_enable_timing", "te_get_timing", "te_get_flag_counters", "te_get_escalation_stats", "te_fused_plan", "te_slope", "te_normals", "te_step", "te_roughness", "te_chain",
+           "te_chain_batched", "te_footprint", "te_footprint2", "te_ipc_export", "te_ipc_open", "te_ipc_close", "te_event_create_ipc", "te_event_open_ipc",
+           "te_event_record", "te_event_destroy", "te_halo_pull", "te_host_alloc", "te_host_free"]
+
+
+IPC_HANDLE_BYTES = 80  # TE_IPC_HANDLE_BYTES
 
 
 class TEError(RuntimeError):
@@ -42,6 +46,11 @@ class Slab(C.Structure):
     _fields_ = [("col_begin", C.c_int32), ("col_count", C.c_int32), ("halo_left", C.c_int32), ("halo_right", C.c_int32)]
 
 
+class HaloPeer(C.Structure):
+    """te_halo_peer: a neighbour's slab buffer as mapped into this process."""
+    _fields_ = [("layer", C.c_void_p), ("slab", Slab), ("ready_event", C.c_void_p)]
+
+
 class ChainParams(C.Structure):
     _fields_ = [("normals_radius", C.c_double), ("normals_algorithm", C.c_int32),
                 ("normals_positive_axis", C.c_int32), ("slope_critical", C.c_double),
@@ -60,7 +69,7 @@ class ChainParams(C.Structure):
 class FootprintParams(C.Structure):
     _fields_ = [("radius", C.c_double), ("offset", C.c_double), ("traversability_default", C.c_double),
                 ("max_gap_width", C.c_double), ("critical_step_height", C.c_double),
-                ("radius_is_integer_norm", C.c_int32), ("reserved0", C.c_int32)]
+                ("radius_is_integer_norm", C.c_int32), ("verify_roughness", C.c_int32)]
 
     @classmethod
     def yaml_defaults(cls):
@@ -110,9 +119,15 @@ def load_library():
         L.te_chain.argtypes = [vp, G, S, P, fp, fp, fp, fp, fp, fp, fp, fp, C.c_int]
         L.te_chain_batched.argtypes = [vp, G, P, C.c_int32, fp, fp, fp, fp, fp, C.c_int]
         L.te_footprint.argtypes = [vp, G, S, F, fp, fp, fp, fp, fp, fp, fp, C.c_int]
+        L.te_footprint2.argtypes = [vp, G, S, F, fp, fp, fp, fp, fp, fp, fp, fp, fp, C.c_int]
         L.te_ipc_export.argtypes = [vp, vp]
         L.te_ipc_open.argtypes = [vp, C.POINTER(vp)]
         L.te_ipc_close.argtypes = [vp]
+        L.te_event_create_ipc.argtypes = [vp, C.POINTER(vp), vp]
+        L.te_event_open_ipc.argtypes = [vp, C.POINTER(vp)]
+        L.te_event_record.argtypes = [vp, vp]
+        L.te_event_destroy.argtypes = [vp]
+        L.te_halo_pull.argtypes = [vp, G, S, fp, C.POINTER(HaloPeer), C.POINTER(HaloPeer)]
         _lib = L
     return _lib
 
@@ -196,6 +211,13 @@ class Context:
         self._check(self._L.te_get_flag_counters(self._h, a))
         return list(a)
 
+    def escalation_stats(self):
+        """(cells by escalation reason [16], cells by number of valid window cells [26]) of the last fused launch."""
+        a, b = (C.c_uint32 * 16)(), (C.c_uint32 * 26)()
+        self._L.te_get_escalation_stats.argtypes = [C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+        self._check(self._L.te_get_escalation_stats(self._h, a, b))
+        return list(a), list(b)
+
     def slope(self, g, critical, nz, out, memory):
         self._check(self._L.te_slope(self._h, C.byref(g), critical, _addr(nz), _addr(out), memory))
 
@@ -218,10 +240,51 @@ class Context:
         self._check(self._L.te_chain_batched(self._h, C.byref(g), C.byref(p), nmaps, _addr(elevation), _addr(slope),
                                              _addr(step), _addr(roughness), _addr(traversability), memory))
 
-    def footprint(self, g, fp, traversability, slope, step, elevation, out, memory, slab=None, slope_fp=None, step_fp=None):
-        self._check(self._L.te_footprint(self._h, C.byref(g), C.byref(slab) if slab is not None else None, C.byref(fp),
-                                         _addr(traversability), _addr(slope), _addr(step), _addr(elevation), _addr(out),
-                                         _addr(slope_fp), _addr(step_fp), memory))
+    def footprint(self, g, fp, traversability, slope, step, elevation, out, memory, slab=None, slope_fp=None, step_fp=None,
+                  roughness=None, roughness_fp=None):
+        if roughness is None and roughness_fp is None:
+            self._check(self._L.te_footprint(self._h, C.byref(g), C.byref(slab) if slab is not None else None, C.byref(fp),
+                                             _addr(traversability), _addr(slope), _addr(step), _addr(elevation), _addr(out),
+                                             _addr(slope_fp), _addr(step_fp), memory))
+        else:
+            self._check(self._L.te_footprint2(self._h, C.byref(g), C.byref(slab) if slab is not None else None, C.byref(fp),
+                                              _addr(traversability), _addr(slope), _addr(step), _addr(roughness), _addr(elevation),
+                                              _addr(out), _addr(slope_fp), _addr(step_fp), _addr(roughness_fp), memory))
+
+    # ---- multi-GPU halo (te_halo_pull and the IPC helpers around it)
+    def ipc_export(self, device_ptr) -> bytes:
+        h = C.create_string_buffer(IPC_HANDLE_BYTES)
+        self._check(self._L.te_ipc_export(_addr(device_ptr), h))
+        return h.raw
+
+    def ipc_open(self, handle: bytes) -> int:
+        out = C.c_void_p()
+        self._check(self._L.te_ipc_open(C.create_string_buffer(handle, IPC_HANDLE_BYTES), C.byref(out)))
+        return out.value
+
+    def ipc_close(self, ptr: int):
+        self._check(self._L.te_ipc_close(ptr))
+
+    def event_create_ipc(self):
+        """(event, 64-byte handle) of an interprocess event recorded with event_record()."""
+        ev, h = C.c_void_p(), C.create_string_buffer(64)
+        self._check(self._L.te_event_create_ipc(self._h, C.byref(ev), h))
+        return ev.value, h.raw
+
+    def event_open_ipc(self, handle: bytes) -> int:
+        ev = C.c_void_p()
+        self._check(self._L.te_event_open_ipc(C.create_string_buffer(handle, 64), C.byref(ev)))
+        return ev.value
+
+    def event_record(self, event: int):
+        self._check(self._L.te_event_record(self._h, event))
+
+    def event_destroy(self, event: int):
+        self._check(self._L.te_event_destroy(event))
+
+    def halo_pull(self, g, slab, layer, left=None, right=None):
+        self._check(self._L.te_halo_pull(self._h, C.byref(g), C.byref(slab), _addr(layer),
+                                         C.byref(left) if left is not None else None, C.byref(right) if right is not None else None))
 
     # Convenience for host numpy layers (column-major float32), used by tests.
     def chain_host(self, g, p, elevation, with_normals=False):

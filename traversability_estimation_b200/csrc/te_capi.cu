@@ -1,12 +1,14 @@
 // te_capi.cu — the extern "C" boundary of libte_b200 (see include/te_b200.h).
 // Host-side responsibilities only: argument validation with the reference's conventions, the
 // per-geometry position tables, host<->device staging for TE_MEM_HOST callers, kernel selection.
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <map>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -61,8 +63,14 @@ inline double cell_coord(double map_pos, double length, double res, int idx) {
   return (map_pos + offset) + res * (-(double)idx);
 }
 
-// Largest index offset that can satisfy the circle test, plus a guard cell.
-inline int reach_generous(double radius, double res) { return (int)std::floor(radius / res) + 1; }
+// Largest index offset that can satisfy the circle test.  A cell at offset R + 1 lies (R + 1) * res from the centre up to a few
+// ulps of the absolute coordinates (~1e-14 m); it can pass `d^2 <= r^2` only if radius / res is within rounding of R + 1, and
+// only then is the guard cell scanned (the literal kernels test every candidate with the reference's own arithmetic anyway).
+inline int reach_generous(double radius, double res) {
+  const double q = radius / res;
+  const int R = (int)std::floor(q);
+  return (q - (double)R > 1.0 - 1e-6) ? R + 1 : R;
+}
 // Dependency radius in cells (what a slab halo must provide).
 inline int reach_true(double radius, double res) { return (int)std::floor(radius / res + 1e-9); }
 
@@ -198,6 +206,7 @@ te::SlabView make_view(te_ctx* c, const te_geometry* g, const te_slab& s) {
   v.X = (const double*)c->dX.p;
   v.Y = (const double*)c->dY.p;
   v.res = g->resolution;
+  v.coord_max = std::max(std::fabs(g->position_x) + 0.5 * g->length_x, std::fabs(g->position_y) + 0.5 * g->length_y);
   return v;
 }
 
@@ -264,10 +273,10 @@ int run_chain_device(te_ctx* c, const te_geometry* g, const te::SlabView& v, con
     if (cap >= ((size_t)1 << 32)) return fail(TE_ERR_UNSUPPORTED, "launch of %zu cells exceeds the work-list index range", cells);
     TE_CUDA(c->worklist.reserve(sizeof(unsigned) * cap));
     TE_CUDA(c->worklist3.reserve(sizeof(unsigned) * cells));
-    TE_CUDA(c->counter.reserve(sizeof(unsigned) * 64));
+    TE_CUDA(c->counter.reserve(sizeof(unsigned) * 128));
     {  // one launch covers every map of the batch
       const te::ChainOut& om = o;
-      TE_CUDA(cudaMemsetAsync(c->counter.p, 0, sizeof(unsigned) * 64, c->stream));
+      TE_CUDA(cudaMemsetAsync(c->counter.p, 0, sizeof(unsigned) * 128, c->stream));
       te_ctx::Ev3* ev = nullptr;
       if (c->timing) {
         if (int rc = next_timing_slot(c, &ev)) return rc;
@@ -374,6 +383,19 @@ int te_destroy(te_ctx* c) {
   return TE_OK;
 }
 
+int te_host_alloc(void** out, size_t bytes) {
+  if (!out) return fail(TE_ERR_BAD_ARG, "out pointer is null");
+  *out = nullptr;
+  TE_CUDA(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault));
+  return TE_OK;
+}
+
+int te_host_free(void* p) {
+  if (!p) return TE_OK;
+  TE_CUDA(cudaFreeHost(p));
+  return TE_OK;
+}
+
 int te_set_stream(te_ctx* c, void* s) {
   TE_ENTER(c);
   c->stream = s ? (cudaStream_t)s : c->own_stream;
@@ -454,6 +476,20 @@ int te_get_flag_counters(te_ctx* c, uint32_t out[5]) {
     out[2] = raw[2] | raw[5];   // a work list overflowed (never: the lists hold every cell of the launch)
     out[4] = raw[4];            // cells tier 2 passed on to the literal kernel
   }
+  return TE_OK;
+}
+
+int te_get_escalation_stats(te_ctx* c, uint32_t reasons[16], uint32_t valid_cells[26]) {
+  TE_ENTER(c);
+  if (!reasons || !valid_cells) return fail(TE_ERR_BAD_ARG, "null argument");
+  unsigned raw[64];
+  std::memset(raw, 0, sizeof(raw));
+  if (c->counter.p) {
+    TE_CUDA(cudaStreamSynchronize(c->stream));
+    TE_CUDA(cudaMemcpy(raw, c->counter.p, sizeof(raw), cudaMemcpyDeviceToHost));
+  }
+  for (int k = 0; k < 16; ++k) reasons[k] = raw[8 + k];
+  for (int k = 0; k < 26; ++k) valid_cells[k] = raw[24 + k];
   return TE_OK;
 }
 
@@ -706,8 +742,9 @@ int te_chain_batched(te_ctx* c, const te_geometry* g, const te_chain_params* p, 
   return chain_common(c, g, nullptr, p, nmaps, elev, slope, step, rough, trav, nullptr, nullptr, nullptr, memory);
 }
 
-int te_footprint(te_ctx* c, const te_geometry* g, const te_slab* slab, const te_footprint_params* p, const float* trav,
-                 const float* slope, const float* step, const float* elev, float* out, float* slope_fp, float* step_fp, int memory) {
+int te_footprint2(te_ctx* c, const te_geometry* g, const te_slab* slab, const te_footprint_params* p, const float* trav,
+                  const float* slope, const float* step, const float* rough, const float* elev, float* out, float* slope_fp,
+                  float* step_fp, float* rough_fp, int memory) {
   TE_ENTER(c);
   if (int rc = check_geometry(g)) return rc;
   if (!p) return fail(TE_ERR_BAD_ARG, "footprint parameters are null");
@@ -716,23 +753,28 @@ int te_footprint(te_ctx* c, const te_geometry* g, const te_slab* slab, const te_
   if (!slope) return fail(TE_ERR_MISSING_LAYER, "layer traversability_slope is missing");
   if (!step) return fail(TE_ERR_MISSING_LAYER, "layer traversability_step is missing");
   if (!elev) return fail(TE_ERR_MISSING_LAYER, "layer elevation is missing");
+  if (p->verify_roughness && !rough) return fail(TE_ERR_MISSING_LAYER, "layer traversability_roughness is missing (verify_roughness is set)");
   if (!out) return fail(TE_ERR_BAD_ARG, "output layer is null");
+  const bool use_rough = p->verify_roughness != 0;
   te_slab s;
   const int need = te::footprint_halo(g, p);
   if (int rc = resolve_slab(g, slab, need, &s)) return rc;
   if (int rc = ensure_geometry(c, g)) return rc;
   const size_t in_bytes = sizeof(float) * (size_t)g->rows * (s.halo_left + s.col_count + s.halo_right);
   const size_t out_bytes = sizeof(float) * (size_t)g->rows * s.col_count;
-  const float* in[4] = {trav, slope, step, elev};
-  float* o[3] = {out, slope_fp, step_fp};
-  float* host_o[3] = {out, slope_fp, step_fp};
+  const float* in[5] = {trav, slope, step, elev, use_rough ? rough : nullptr};
+  float* o[4] = {out, slope_fp, step_fp, use_rough ? rough_fp : nullptr};
+  float* host_o[4] = {out, slope_fp, step_fp, use_rough ? rough_fp : nullptr};
   if (memory == TE_MEM_HOST) {
-    for (int k = 0; k < 4; ++k) {
-      TE_CUDA(c->stage[k].reserve(in_bytes));
-      TE_CUDA(cudaMemcpyAsync(c->stage[k].p, in[k], in_bytes, cudaMemcpyHostToDevice, c->stream));
-      in[k] = (const float*)c->stage[k].p;
+    // staging: inputs 0..3 (+ roughness in slot 11), outputs 4..7
+    const int slot_in[5] = {0, 1, 2, 3, 11};
+    for (int k = 0; k < 5; ++k) {
+      if (!in[k]) continue;
+      TE_CUDA(c->stage[slot_in[k]].reserve(in_bytes));
+      TE_CUDA(cudaMemcpyAsync(c->stage[slot_in[k]].p, in[k], in_bytes, cudaMemcpyHostToDevice, c->stream));
+      in[k] = (const float*)c->stage[slot_in[k]].p;
     }
-    for (int k = 0; k < 3; ++k) {
+    for (int k = 0; k < 4; ++k) {
       if (!host_o[k]) continue;
       TE_CUDA(c->stage[4 + k].reserve(out_bytes));
       o[k] = (float*)c->stage[4 + k].p;
@@ -740,39 +782,151 @@ int te_footprint(te_ctx* c, const te_geometry* g, const te_slab* slab, const te_
   }
   const te::SlabView v = make_view(c, g, s);
   int nl = 0;
-  int rc = te::launch_footprint(c->fp, v, g, p, c->hX, c->hY, in[0], in[1], in[2], in[3], o[0], o[1], o[2], c->sms, c->stream, &nl);
+  int rc = te::launch_footprint(c->fp, v, g, p, c->hX, c->hY, in[0], in[1], in[2], in[4], in[3], o[0], o[1], o[2], o[3], c->sms,
+                                c->stream, &nl);
   if (rc != 0) return fail(rc, "footprint sweep failed: %s", c->fp.why.c_str());
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(TE_ERR_CUDA, "footprint launch failed: %s", cudaGetErrorString(e));
   c->launches += nl;
   if (memory == TE_MEM_HOST) {
-    for (int k = 0; k < 3; ++k)
+    for (int k = 0; k < 4; ++k)
       if (host_o[k]) TE_CUDA(cudaMemcpyAsync(host_o[k], o[k], out_bytes, cudaMemcpyDeviceToHost, c->stream));
     TE_CUDA(cudaStreamSynchronize(c->stream));
   }
   return TE_OK;
 }
 
+int te_footprint(te_ctx* c, const te_geometry* g, const te_slab* slab, const te_footprint_params* p, const float* trav,
+                 const float* slope, const float* step, const float* elev, float* out, float* slope_fp, float* step_fp, int memory) {
+  if (p && p->verify_roughness) return fail(TE_ERR_MISSING_LAYER, "verify_roughness is set: call te_footprint2 with the traversability_roughness layer");
+  return te_footprint2(c, g, slab, p, trav, slope, step, nullptr, elev, out, slope_fp, step_fp, nullptr, memory);
+}
+
+// A te IPC handle is the CUDA handle of the ALLOCATION that contains the pointer (cudaIpcGetMemHandle always describes the whole
+// allocation; sub-allocating pools such as torch's caching allocator hand out interior pointers) plus the offset into it.
+struct TeIpcHandle {
+  cudaIpcMemHandle_t mem;
+  uint64_t offset;
+  uint64_t reserved;
+};
+static_assert(sizeof(TeIpcHandle) == TE_IPC_HANDLE_BYTES, "te IPC handle layout");
+
+namespace {
+std::mutex g_ipc_mu;
+std::map<void*, void*> g_ipc_opened;  // pointer handed out by te_ipc_open -> base of the mapping to close
+}  // namespace
+
 int te_ipc_export(const void* device_ptr, void* handle) {
   if (!device_ptr || !handle) return fail(TE_ERR_BAD_ARG, "null argument");
-  cudaIpcMemHandle_t h;
-  TE_CUDA(cudaIpcGetMemHandle(&h, const_cast<void*>(device_ptr)));
-  static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  typedef CUresult (*PFN_range)(CUdeviceptr*, size_t*, CUdeviceptr);
+  static PFN_range range = nullptr;
+  if (!range) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+      return fail(TE_ERR_CUDA, "cuMemGetAddressRange entry point unavailable");
+    range = reinterpret_cast<PFN_range>(p);
+  }
+  CUdeviceptr base = 0;
+  size_t size = 0;
+  if (range(&base, &size, (CUdeviceptr)device_ptr) != CUDA_SUCCESS) return fail(TE_ERR_CUDA, "cuMemGetAddressRange failed (not a device allocation?)");
+  TeIpcHandle h{};
+  TE_CUDA(cudaIpcGetMemHandle(&h.mem, reinterpret_cast<void*>(base)));
+  h.offset = (uint64_t)((CUdeviceptr)device_ptr - base);
   std::memcpy(handle, &h, sizeof(h));
   return TE_OK;
 }
 
 int te_ipc_open(const void* handle, void** out) {
   if (!handle || !out) return fail(TE_ERR_BAD_ARG, "null argument");
-  cudaIpcMemHandle_t h;
+  TeIpcHandle h;
   std::memcpy(&h, handle, sizeof(h));
-  TE_CUDA(cudaIpcOpenMemHandle(out, h, cudaIpcMemLazyEnablePeerAccess));
+  void* base = nullptr;
+  TE_CUDA(cudaIpcOpenMemHandle(&base, h.mem, cudaIpcMemLazyEnablePeerAccess));
+  *out = (char*)base + h.offset;
+  std::lock_guard<std::mutex> lock(g_ipc_mu);
+  g_ipc_opened[*out] = base;
   return TE_OK;
 }
 
 int te_ipc_close(void* p) {
   if (!p) return TE_OK;
-  TE_CUDA(cudaIpcCloseMemHandle(p));
+  void* base = p;
+  {
+    std::lock_guard<std::mutex> lock(g_ipc_mu);
+    auto it = g_ipc_opened.find(p);
+    if (it != g_ipc_opened.end()) { base = it->second; g_ipc_opened.erase(it); }
+  }
+  TE_CUDA(cudaIpcCloseMemHandle(base));
+  return TE_OK;
+}
+
+int te_event_create_ipc(te_ctx* c, void** event_out, void* handle) {
+  TE_ENTER(c);
+  if (!event_out || !handle) return fail(TE_ERR_BAD_ARG, "null argument");
+  cudaEvent_t ev;
+  TE_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming | cudaEventInterprocess));
+  cudaIpcEventHandle_t h;
+  cudaError_t e = cudaIpcGetEventHandle(&h, ev);
+  if (e != cudaSuccess) {
+    cudaEventDestroy(ev);
+    return fail(TE_ERR_CUDA, "cudaIpcGetEventHandle failed: %s", cudaGetErrorString(e));
+  }
+  static_assert(sizeof(h) == 64, "cudaIpcEventHandle_t is 64 bytes");
+  std::memcpy(handle, &h, sizeof(h));
+  *event_out = (void*)ev;
+  return TE_OK;
+}
+
+int te_event_open_ipc(const void* handle, void** event_out) {
+  if (!handle || !event_out) return fail(TE_ERR_BAD_ARG, "null argument");
+  cudaIpcEventHandle_t h;
+  std::memcpy(&h, handle, sizeof(h));
+  cudaEvent_t ev;
+  TE_CUDA(cudaIpcOpenEventHandle(&ev, h));
+  *event_out = (void*)ev;
+  return TE_OK;
+}
+
+int te_event_record(te_ctx* c, void* event) {
+  TE_ENTER(c);
+  if (!event) return fail(TE_ERR_BAD_ARG, "event is null");
+  TE_CUDA(cudaEventRecord((cudaEvent_t)event, c->stream));
+  return TE_OK;
+}
+
+int te_event_destroy(void* event) {
+  if (!event) return TE_OK;
+  TE_CUDA(cudaEventDestroy((cudaEvent_t)event));
+  return TE_OK;
+}
+
+int te_halo_pull(te_ctx* c, const te_geometry* g, const te_slab* slab, float* layer, const te_halo_peer* left,
+                 const te_halo_peer* right) {
+  TE_ENTER(c);
+  if (int rc = check_geometry(g)) return rc;
+  if (!slab || !layer) return fail(TE_ERR_BAD_ARG, "null argument");
+  te_slab s;
+  if (int rc = resolve_slab(g, slab, 0, &s)) return rc;
+  const size_t col_bytes = sizeof(float) * (size_t)g->rows;
+  // Global columns [first, first + count) into this rank's buffer, from the OWNED columns of `p`.
+  auto pull = [&](const te_halo_peer* p, int first, int count, const char* side) -> int {
+    if (count <= 0) return TE_OK;
+    if (!p || !p->layer) return fail(TE_ERR_BAD_ARG, "slab has a %s halo of %d columns but no %s neighbour was given", side, count, side);
+    const te_slab& q = p->slab;
+    if (q.col_begin < 0 || q.col_count <= 0 || q.halo_left < 0 || q.halo_right < 0 || q.col_begin + q.col_count > g->cols)
+      return fail(TE_ERR_BAD_ARG, "%s neighbour's slab is malformed", side);
+    if (first < q.col_begin || first + count > q.col_begin + q.col_count)
+      return fail(TE_ERR_BAD_ARG, "%s halo columns [%d,%d) are not owned by the %s neighbour [%d,%d): the exchange is one hop", side,
+                  first, first + count, side, q.col_begin, q.col_begin + q.col_count);
+    if (p->ready_event) TE_CUDA(cudaStreamWaitEvent(c->stream, (cudaEvent_t)p->ready_event, 0));
+    const char* src = (const char*)p->layer + col_bytes * (size_t)(first - (q.col_begin - q.halo_left));
+    char* dst = (char*)layer + col_bytes * (size_t)(first - (s.col_begin - s.halo_left));
+    TE_CUDA(cudaMemcpyAsync(dst, src, col_bytes * (size_t)count, cudaMemcpyDefault, c->stream));
+    return TE_OK;
+  };
+  if (int rc = pull(left, s.col_begin - s.halo_left, s.halo_left, "left")) return rc;
+  if (int rc = pull(right, s.col_begin + s.col_count, s.halo_right, "right")) return rc;
   return TE_OK;
 }
 

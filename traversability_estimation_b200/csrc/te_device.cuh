@@ -18,6 +18,8 @@ struct SlabView {
   const double* X;  // [rows]
   const double* Y;  // [cols_total]
   double res;
+  double coord_max;  // largest |cell-centre coordinate| of the global map (host-side use: error bounds of the reference's
+                     // absolute-coordinate arithmetic)
 };
 
 // Chain parameters in the form the kernels want them.

@@ -47,8 +47,9 @@ __device__ float step_height_t2(const FixupArgs& A, const Elev& E, int a, int b)
   return (float)((double)mx - (double)mn);
 }
 
-// pass 2 of StepFilter.cpp:147-178
-__device__ float step_t2(const FixupArgs& A, const Elev& E, int i, int j) {
+// pass 2 of StepFilter.cpp:147-178.  Out of line and with its arguments BY VALUE: the step part is needed for the rare cells an
+// infinite elevation reaches, and a reference to the kernel parameters would force them into local memory for every thread.
+__device__ __noinline__ float step_t2(const FixupArgs A, const Elev E, int i, int j) {
   const unsigned rm = A.rowmask ? A.rowmask[i] : 0u, cm = A.colmask ? A.colmask[j] : 0u;
   double stepMax = 0.0;
   int n = 0;
@@ -75,41 +76,59 @@ __device__ float step_t2(const FixupArgs& A, const Elev& E, int i, int j) {
   return (float)(step < A.step_crit ? 1.0 - step / A.step_crit : 0.0);
 }
 
+// 1/n, correctly rounded, for the valid-cell counts a 5 x 5 window can have (constant memory: indexed dynamically)
+__constant__ double c_rcp[26] = {0.0,      1.0 / 1,  1.0 / 2,  1.0 / 3,  1.0 / 4,  1.0 / 5,  1.0 / 6,  1.0 / 7,  1.0 / 8,
+                                 1.0 / 9,  1.0 / 10, 1.0 / 11, 1.0 / 12, 1.0 / 13, 1.0 / 14, 1.0 / 15, 1.0 / 16, 1.0 / 17,
+                                 1.0 / 18, 1.0 / 19, 1.0 / 20, 1.0 / 21, 1.0 / 22, 1.0 / 23, 1.0 / 24, 1.0 / 25};
+
+// acos on [0,1] in float32: sqrt(1-x) * P7(x), the same polynomial tier 1 evaluates (te_fused.cu acos2; max abs error 2.2e-7,
+// max rel. error 1.7e-7 — 1 - x is exact, so the relative accuracy holds down to theta -> 0).  The argument is the float32 n_z
+// the reference reads back from the layer (SlopeFilter.cpp:74).
+__device__ __forceinline__ float acos_t2(float x) {
+  const float u = 1.0f - x;
+  float p = fmaf(x, -0.0011488182935863733f, 0.006254698149859905f);
+  p = fmaf(p, x, -0.016484638676047325f);
+  p = fmaf(p, x, 0.03044925443828106f);
+  p = fmaf(p, x, -0.05000271648168564f);
+  p = fmaf(p, x, 0.08894557505846024f);
+  p = fmaf(p, x, -0.21459604799747467f);
+  p = fmaf(p, x, 1.570796251296997f);
+  return sqrtf(u) * p;
+}
+
 // Normals + slope + roughness of one cell in fp64 on centred coordinates.  Returns false when the
 // result cannot be certified at this tier.
+// `why` receives the reason of an escalation (1 degenerate full window, 2 rank of a full window, 3 eigen-gap of a full window,
+// 4 no convergence, 5 rank of a partial window, 6 conditioning of a partial window, 7 null eigenvector, 8 n_z == 0,
+// 9 n_z on a float32 rounding boundary) in its low byte and the number of valid window cells in the next one.
 __device__ bool normals_t2(const FixupArgs& A, const Elev& E, int i, int j, float& fnx, float& fny, float& fnz, float& slope,
-                           float& rough) {
+                           float& rough, unsigned& why) {
   const float zc = E(i, j);
   if (!finitef(zc)) {  // hole: no normal, slope and roughness stay NaN (SlopeFilter.cpp:71, RoughnessFilter.cpp:84)
     fnx = fny = fnz = slope = rough = nanf_();
     return true;
   }
-  // gather the 5 x 5 neighbourhood with 25 unconditional, independent loads, then work from registers without branches.
-  // A cell that is outside the map / window / buffer or not finite is replaced by the centre value (so its deviation below
-  // is an exact zero) and stays out of the validity mask (bit (l+2)*5 + (k+2)).
-  float zw[5][5];
+  // Gather the 5 x 5 neighbourhood with 25 unconditional, independent loads and accumulate the four moments that involve z on
+  // the fly (no array: nothing lives in local memory).  A cell that is outside the map / window / buffer or not finite is
+  // replaced by the centre value (its deviation is an exact zero) and stays out of the validity mask (bit (l+2)*5 + (k+2)).
   unsigned mask = 0;
+  double sw = 0, suw = 0, svw = 0, sww = 0;
   {
     const int lb0 = j - A.in_col0;
+    const double dzc = (double)zc;
     unsigned shape = 0;  // cells of the disk window
 #pragma unroll
     for (int l = -2; l <= 2; ++l) {
       const int w = A.wn[l < 0 ? -l : l];
-#pragma unroll
-      for (int k = -2; k <= 2; ++k) shape |= (k >= -w && k <= w) ? (1u << ((l + 2) * 5 + (k + 2))) : 0u;
+      shape |= (w >= 2 ? 0x1fu : w == 1 ? 0x0eu : w == 0 ? 0x04u : 0u) << ((l + 2) * 5);
     }
+    float v[5][5];
     if (i >= 2 && i + 2 < A.rows && j >= 2 && j + 2 < A.cols_total && lb0 >= 2 && lb0 + 2 < A.in_ncols) {
       const float* base = E.e + (size_t)lb0 * A.rows + i;  // interior cell: no clamping
 #pragma unroll
       for (int l = -2; l <= 2; ++l)
 #pragma unroll
-        for (int k = -2; k <= 2; ++k) {
-          const float v = __ldg(base + (ptrdiff_t)l * A.rows + k);
-          const unsigned bitm = 1u << ((l + 2) * 5 + (k + 2));
-          const bool ok = (shape & bitm) != 0u && finitef(v);
-          zw[l + 2][k + 2] = ok ? v : zc;
-          mask |= ok ? bitm : 0u;
-        }
+        for (int k = -2; k <= 2; ++k) v[l + 2][k + 2] = __ldg(base + (ptrdiff_t)l * A.rows + k);
     } else {
 #pragma unroll
       for (int l = -2; l <= 2; ++l) {
@@ -119,17 +138,32 @@ __device__ bool normals_t2(const FixupArgs& A, const Elev& E, int i, int j, floa
 #pragma unroll
         for (int k = -2; k <= 2; ++k) {
           const int a = i + k;
-          const float v = __ldg(col + min(max(a, 0), A.rows - 1));
-          const unsigned bitm = 1u << ((l + 2) * 5 + (k + 2));
-          const bool ok = col_ok && a >= 0 && a < A.rows && (shape & bitm) != 0u && finitef(v);
-          zw[l + 2][k + 2] = ok ? v : zc;
-          mask |= ok ? bitm : 0u;
+          const float x = __ldg(col + min(max(a, 0), A.rows - 1));
+          v[l + 2][k + 2] = (col_ok && a >= 0 && a < A.rows) ? x : nanf_();
         }
       }
     }
+#pragma unroll
+    for (int l = -2; l <= 2; ++l) {
+      double cs = 0.0, ck = 0.0;  // column sums of d and k*d
+#pragma unroll
+      for (int k = -2; k <= 2; ++k) {
+        const unsigned bitm = 1u << ((l + 2) * 5 + (k + 2));
+        const bool ok = finitef(v[l + 2][k + 2]) && (shape & bitm) != 0u;
+        mask |= ok ? bitm : 0u;
+        const double d = (double)(ok ? v[l + 2][k + 2] : zc) - dzc;  // invalid cells: exact zero
+        cs += d;
+        if (k != 0) ck = fma((double)k, d, ck);
+        sww = fma(d, d, sww);
+      }
+      sw += cs;
+      suw += ck;
+      if (l != 0) svw = fma((double)l, cs, svw);
+    }
+    suw *= -A.res;  // u = -res*k, v = -res*l
+    svw *= -A.res;
   }
-  // The moments of the cell offsets depend only on WHICH cells are valid: integer sums over the 25-bit validity mask,
-  // exact, instead of 25 x 6 fp64 accumulations.  Only the four moments that involve z are summed.
+  // The moments of the cell offsets depend only on WHICH cells are valid: integer sums over the 25-bit validity mask, exact.
   constexpr unsigned KM = 0x108421u, LM = 0x1fu;  // cells of row offset k = -2 / of column offset l = -2
   const int k_m2 = __popc(mask & KM), k_m1 = __popc(mask & (KM << 1)), k_p1 = __popc(mask & (KM << 3)), k_p2 = __popc(mask & (KM << 4));
   const int l_m2 = __popc(mask & LM), l_m1 = __popc(mask & (LM << 5)), l_p1 = __popc(mask & (LM << 15)), l_p2 = __popc(mask & (LM << 20));
@@ -142,60 +176,59 @@ __device__ bool normals_t2(const FixupArgs& A, const Elev& E, int i, int j, floa
   const int ikl = (__popc(mask & kl_p1) - __popc(mask & kl_m1)) + 2 * (__popc(mask & kl_p2) - __popc(mask & kl_m2)) +
                   4 * (__popc(mask & kl_p4) - __popc(mask & kl_m4));
   const double res2 = A.res * A.res;
-  const double n = (double)__popc(mask);
-  const double su = -A.res * (double)ik, sv = -A.res * (double)il;  // u = -res*k, v = -res*l
+  const int cnt = __popc(mask);
+  const double n = (double)cnt;
+  const double su = -A.res * (double)ik, sv = -A.res * (double)il;
   const double suu = res2 * (double)ikk, svv = res2 * (double)ill, suv = res2 * (double)ikl;
-  double sw = 0, suw = 0, svw = 0, sww = 0;
-#pragma unroll
-  for (int l = -2; l <= 2; ++l)
-#pragma unroll
-    for (int k = -2; k <= 2; ++k) {
-      const double d = (double)zw[l + 2][k + 2] - (double)zc;  // invalid cells: exact zero
-      sw += d;
-      if (k != 0) suw = fma(-A.res * (double)k, d, suw);
-      if (l != 0) svw = fma(-A.res * (double)l, d, svw);
-      sww = fma(d, d, sww);
-    }
   double nx = 0.0, ny = 0.0, nz = 1.0;
-  const double rn = 1.0 / n;
+  const double rn = c_rcp[cnt];  // 1/n, correctly rounded
   const double mu = su * rn, mv = sv * rn, mw = sw * rn;
   // scatter matrix sum (p - mean)(p - mean)^T
   const double xx = fma(-su, mu, suu), xy = fma(-su, mv, suv), xz = fma(-su, mw, suw);
   const double yy = fma(-sv, mv, svv), yz = fma(-sv, mw, svw), zz = fma(-sw, mw, sww);
-  if (n >= 3.0 && zz > 0.0) {
+  if (cnt >= 3 && zz > 0.0) {
     double bx, by, bz;
-    if (n == A.n_full) {
+    if (cnt == A.n_full_i) {
       // full disk window: scatter = [[a,0,p],[0,a,q],[p,q,c]] (sums of u, v, uv vanish by symmetry) and
       // the eigen-problem collapses to 2x2 — robust even when two eigenvalues nearly coincide
       const double a = 0.5 * (xx + yy), g2 = fma(xz, xz, yz * yz);
-      const double h = 0.5 * (a - zz), D = sqrt(fma(h, h, g2));
+      const double h = 0.5 * (a - zz), hh = fma(h, h, g2);
+      const double D = sqrt(hh);
       const double dph = D + fabs(h);
+      why = 1u | ((unsigned)cnt << 8);
       if (!(dph > 0.0)) return false;
       const double qq = g2 / dph;
       const double m = h >= 0.0 ? dph : qq;           // a - lambda0
       const double lam = (h >= 0.0 ? zz : a) - qq;     // lambda0
       const double big = fmax(a, zz);
+      why = 2u | ((unsigned)cnt << 8);
       if (!(lam > 1e-9 * big)) return false;           // rank: the literal QR decides (tier 3)
+      why = 3u | ((unsigned)cnt << 8);
       if (!(fmin(2.0 * D, m) > 1e-7 * big)) return false;
       bx = -xz; by = -yz; bz = m;
     } else {
       const double c2 = xx + yy + zz;
       const double c1 = xx * yy + xx * zz + yy * zz - xy * xy - xz * xz - yz * yz;
       const double c0 = xx * (yy * zz - yz * yz) - xy * (xy * zz - yz * xz) + xz * (xy * yz - yy * xz);
+      // smallest root of p(l) = -l^3 + c2 l^2 - c1 l + c0 (three real non-negative roots): Halley from 0 converges monotonically
+      // from below and cubically — three or four iterations where Newton took six to ten, one division each
       double lam = 0.0, dp = -c1;
       bool conv = false;
 #pragma unroll 1
-      for (int it = 0; it < 40; ++it) {  // Newton from below: monotone convergence to the smallest root
-        const double p = fma(fma(c2 - lam, lam, -c1), lam, c0);
+      for (int it = 0; it < 40; ++it) {
+        const double pv = fma(fma(c2 - lam, lam, -c1), lam, c0);
         dp = fma(fma(-3.0, lam, 2.0 * c2), lam, -c1);
-        if (dp == 0.0) break;
-        const double step = p / dp;
+        const double hpp = fma(-3.0, lam, c2);                   // p''/2
+        const double den = fma(dp, dp, -pv * hpp);               // p'^2 - p p''/2  (> 0 below the smallest root)
+        if (!(den > 0.0)) break;
+        const double step = pv * dp / den;                       // Halley: p p' / (p'^2 - p p''/2), negative (p > 0 > p')
         lam -= step;
         if (fabs(step) <= 1e-15 * c2) { conv = true; break; }
       }
       dp = fma(fma(-3.0, lam, 2.0 * c2), lam, -c1);
       // rank: lambda0 at the reference's rank-threshold scale -> the literal QR decides (tier 3);
       // conditioning: |p'(lambda0)| = (l1 - l0)(l2 - l0) must leave the cross products accurate
+      why = (!conv ? 4u : !(lam > 1e-9 * c2) ? 5u : 6u) | ((unsigned)cnt << 8);
       if (!conv || !(lam > 1e-9 * c2) || !(fabs(dp) > 1e-4 * c2 * c2)) return false;
       const double ax = xx - lam, ay = yy - lam, az = zz - lam;
       // eigenvector = largest cross product of two rows of (S - lambda0 I)
@@ -209,33 +242,40 @@ __device__ bool normals_t2(const FixupArgs& A, const Elev& E, int i, int j, floa
       if (q2 > bq) { bx = v2x; by = v2y; bz = v2z; bq = q2; }
     }
     const double bq = fma(bx, bx, fma(by, by, bz * bz));
+    why = 7u | ((unsigned)cnt << 8);
     if (!(bq > 0.0)) return false;
-    const double inv = 1.0 / sqrt(bq);
+    const double inv = rsqrt(bq);
     nx = bx * inv; ny = by * inv; nz = bz * inv;
     if (nz < 0.0) { nx = -nx; ny = -ny; nz = -nz; }
+    why = 8u | ((unsigned)cnt << 8);
     if (nz == 0.0) return false;
-    // float32 rounding of n_z: where acos amplifies one ulp beyond the tolerance (theta < ~0.02 rad) the
-    // rounding must be certain: escalate when n_z is within 1e-4 ulp of a rounding boundary (tier-2 error ~2e-6 ulp)
+    // float32 rounding of n_z: where acos amplifies one ulp beyond the tolerance (theta < ~0.02 rad) the rounding must be
+    // certain: escalate when n_z is within A.nz_guard ulps of a rounding boundary (make_fixup_args: 100 x the error the
+    // reference's absolute-coordinate arithmetic can carry into its own n_z)
     if (nz > 0.9998) {
       const float f = (float)nz;
       const float up = __uint_as_float(__float_as_uint(f) + 1u), dn = __uint_as_float(__float_as_uint(f) - 1u);
       const double bu = 0.5 * ((double)f + (double)up), bd = 0.5 * ((double)f + (double)dn);
-      const double guard = 1e-4 * (bu - bd);
+      const double guard = A.nz_guard * (bu - bd);
+      why = 9u | ((unsigned)cnt << 8);
       if (fabs(nz - bu) < guard || fabs(nz - bd) < guard) return false;
     }
-  } else if (n >= 3.0) {
-    // exactly flat window: scatter has an exact zero row -> rank 2 -> (0,0,1) in the reference too
   }
   fnx = (float)nx; fny = (float)ny; fnz = (float)nz;
-  const double th = acos((double)fnz);
-  slope = (float)(th < A.slope_crit ? 1.0 - th / A.slope_crit : 0.0);
-  // roughness with the float32 normal (RoughnessFilter.cpp:108-117)
+  // layer = x < crit ? 1 - x/crit : 0 in double, narrowed on store (SlopeFilter.cpp:74-81); 1/crit is a host-side constant
+  const double th = (double)acos_t2(fminf(fnz, 1.0f));
+  slope = (float)(th < A.slope_crit ? fma(-th, A.inv_slope_crit, 1.0) : 0.0);
+  // roughness with the float32 normal (RoughnessFilter.cpp:108-117): the sum over the window of (N . (p - mean))^2 is the
+  // quadratic form N^T S N of the scatter matrix already at hand (the reference sums it point by point; the quadratic form
+  // loses at most ~1e-16 * |S| absolutely, ~1e-12 of the layer value)
   const double NX = fnx, NY = fny, NZ = fnz;
-  // sum over the window of (N . (p - mean))^2 = N^T S N with the scatter matrix S already at hand (RoughnessFilter.cpp
-  // sums it point by point; the quadratic form loses at most ~1e-16 * |S| absolutely, ~1e-12 of the layer value)
   const double sum = fmax(NX * (NX * xx + 2.0 * (NY * xy + NZ * xz)) + NY * (NY * yy + 2.0 * NZ * yz) + NZ * NZ * zz, 0.0);
-  const double r = sqrt(sum / (n - 1.0));  // one point: 0/0 = NaN -> comparison false -> 0.0
-  rough = (float)(r < A.rough_crit ? 1.0 - r / A.rough_crit : 0.0);
+  if (cnt >= 2) {
+    const double r = sqrt(sum * c_rcp[cnt - 1]);
+    rough = (float)(r < A.rough_crit ? fma(-r, A.inv_rough_crit, 1.0) : 0.0);
+  } else {
+    rough = 0.0f;  // one point: 0/0 = NaN -> comparison false -> 0.0 (RoughnessFilter.cpp:117-124)
+  }
   return true;
 }
 
@@ -255,9 +295,10 @@ __global__ void __launch_bounds__(128, 6) k_fixup_t2(FixupArgs A, const float* _
     const bool do_n = (w >> 30) & 1u, do_s = (w >> 31) & 1u;
     float s, r, t;
     bool escalate = false;
+    unsigned why = 0;
     if (do_n) {
       float fx, fy, fz;
-      if (normals_t2(A, E, i, j, fx, fy, fz, s, r)) {
+      if (normals_t2(A, E, i, j, fx, fy, fz, s, r, why)) {
         o.slope[c] = s;
         o.rough[c] = r;
         if (o.nx) { o.nx[c] = fx; o.ny[c] = fy; o.nz[c] = fz; }
@@ -278,6 +319,8 @@ __global__ void __launch_bounds__(128, 6) k_fixup_t2(FixupArgs A, const float* _
       const unsigned idx = atomicAdd(count3, 1u);
       if (idx < cap3) list3[idx] = c | (1u << 30);  // tier 3 redoes the normals part and re-fuses
       else atomicExch(count3 + 1, 1u);              // cannot happen: list3 holds every cell of the launch
+      atomicAdd(count3 + 4 + (why & 15u), 1u);       // diagnostics (te_get_escalation_stats): by reason ...
+      atomicAdd(count3 + 20 + min((why >> 8) & 31u, 25u), 1u);  // ... and by number of valid window cells
     } else {
       o.trav[c] = __fmul_rn(A.fuse_w, __fadd_rn(__fadd_rn(s, t), r));
     }

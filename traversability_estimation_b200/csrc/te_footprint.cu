@@ -27,6 +27,7 @@ struct Layers {
   const float* __restrict__ slope;
   const float* __restrict__ step;
   const float* __restrict__ elev;
+  const float* __restrict__ rough;  // traversability_roughness, only read when verify_rough is set
 };
 
 struct FpArgs {
@@ -36,6 +37,7 @@ struct FpArgs {
   const double* Y;
   double rmin, rmax, rmax2, tdefault, maxgap, crit;
   int int_norm;
+  int verify_rough;  // checkForRoughness_ (TraversabilityMap.cpp:779)
   int n_spiral;
   const int* spiral;  // di & 0xff | (dj & 0xff) << 8 | edge << 16
   int slope_R, step_R;
@@ -113,6 +115,19 @@ __device__ bool check_slope_d(const FpArgs& A, const Layers& L, int i, int j) {
   int n = 0;
   for_circle_d(A, i, j, windowRadius * windowRadius, A.slope_R, [&](int a, int b) {
     if (lay(A, L.slope, a, b) == 0.0f) ++n;
+  });
+  return !(n > nCrit);
+}
+
+// TraversabilityMap::checkForRoughness, TraversabilityMap.cpp:895-921 (the slope check on another layer with another count).
+__device__ bool check_rough_d(const FpArgs& A, const Layers& L, int i, int j) {
+  if (!(lay(A, L.rough, i, j) == 0.0f)) return true;
+  const double windowRadius = 3.0 * A.res;
+  const double criticalLength = A.maxgap / 3.0;
+  const int nCrit = (int)floor(1.5 * windowRadius * criticalLength / (A.res * A.res));
+  int n = 0;
+  for_circle_d(A, i, j, windowRadius * windowRadius, A.slope_R, [&](int a, int b) {
+    if (lay(A, L.rough, a, b) == 0.0f) ++n;
   });
   return !(n > nCrit);
 }
@@ -210,7 +225,8 @@ __device__ bool check_step_d(const FpArgs& A, const Layers& L, int i, int j) {
 }
 
 // blocked[] covers the whole input buffer (columns in_col0 .. in_col0+in_ncols).
-__global__ void __launch_bounds__(128) k_predicates(FpArgs A, Layers L, unsigned char* __restrict__ blocked, float* slope_fp, float* step_fp) {
+__global__ void __launch_bounds__(128) k_predicates(FpArgs A, Layers L, unsigned char* __restrict__ blocked, float* slope_fp, float* step_fp,
+                                                    float* rough_fp) {
   const long long total = (long long)A.rows * A.in_ncols;
   for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < total; c += (long long)gridDim.x * blockDim.x) {
     const int i = (int)(c % A.rows);
@@ -223,12 +239,19 @@ __global__ void __launch_bounds__(128) k_predicates(FpArgs A, Layers L, unsigned
       t_ok = check_step_d(A, L, i, j);
       if (lay(A, L.step, i, j) == 0.0f) tfp = t_ok ? 1.0f : 0.0f;
     }
-    blocked[c] = (s_ok && t_ok) ? 0 : 1;
+    bool r_ok = true;
+    float rfp = nanf_();
+    if (A.verify_rough && s_ok && t_ok) {  // TraversabilityMap.cpp:779-783: only after slope and step passed
+      r_ok = check_rough_d(A, L, i, j);
+      if (lay(A, L.rough, i, j) == 0.0f) rfp = r_ok ? 1.0f : 0.0f;
+    }
+    blocked[c] = (s_ok && t_ok && r_ok) ? 0 : 1;
     const int oj = j - A.out_col0;
     if (oj >= 0 && oj < A.out_ncols) {
       const size_t oc = (size_t)oj * A.rows + i;
       if (slope_fp) slope_fp[oc] = sfp;
       if (step_fp) step_fp[oc] = tfp;
+      if (rough_fp) rough_fp[oc] = rfp;
     }
   }
 }
@@ -496,8 +519,8 @@ int footprint_halo(const te_geometry* g, const te_footprint_params* p) {
 
 int launch_footprint(FootprintState& st, const SlabView& v, const te_geometry* g, const te_footprint_params* p,
                      const std::vector<double>& X, const std::vector<double>& Y, const float* trav, const float* slope,
-                     const float* step, const float* elev, float* out, float* slope_fp, float* step_fp, int sms, cudaStream_t s,
-                     int* launches) {
+                     const float* step, const float* rough, const float* elev, float* out, float* slope_fp, float* step_fp,
+                     float* rough_fp, int sms, cudaStream_t s, int* launches) {
   (void)X; (void)Y;
   const double rmax = p->radius + p->offset;
   if (std::ceil(rmax / g->resolution) > 120.0) { st.why = "footprint radius exceeds 120 cells"; return TE_ERR_UNSUPPORTED; }
@@ -533,14 +556,15 @@ int launch_footprint(FootprintState& st, const SlabView& v, const te_geometry* g
   a.X = v.X; a.Y = v.Y;
   a.rmin = p->radius; a.rmax = rmax; a.rmax2 = rmax * rmax; a.tdefault = p->traversability_default;
   a.maxgap = p->max_gap_width; a.crit = p->critical_step_height; a.int_norm = p->radius_is_integer_norm;
+  a.verify_rough = (p->verify_roughness != 0 && rough != nullptr) ? 1 : 0;
   a.n_spiral = st.n_spiral; a.spiral = (const int*)st.d_spiral;
   a.slope_R = (int)std::floor(3.0 * g->resolution / g->resolution) + 1;
   a.step_R = (int)std::floor(2.5 * g->resolution / g->resolution) + 1;
-  const Layers L{trav, slope, step, elev};
+  const Layers L{trav, slope, step, elev, rough};
   const long long t1 = (long long)ncell_in, t2 = (long long)v.rows * v.out_ncols;
   const int g1 = (int)std::min<long long>((t1 + 127) / 128, (long long)sms * 16);
   const int g2 = (int)std::min<long long>((t2 + 255) / 256, (long long)sms * 8);
-  k_predicates<<<std::max(g1, 1), 128, 0, s>>>(a, L, (unsigned char*)st.d_block, slope_fp, step_fp);
+  k_predicates<<<std::max(g1, 1), 128, 0, s>>>(a, L, (unsigned char*)st.d_block, slope_fp, step_fp, rough_fp);
   const int Lmax = (int)std::floor(rmax / g->resolution + 1e-9);
   const bool fast = Lmax <= 31 && std::getenv("TE_FOOTPRINT_BRUTE") == nullptr;
   if (!fast) {

@@ -35,7 +35,7 @@ int footprint_halo(const te_geometry* g, const te_footprint_params* p);
 
 int launch_footprint(FootprintState& st, const SlabView& v, const te_geometry* g, const te_footprint_params* p,
                      const std::vector<double>& X, const std::vector<double>& Y, const float* trav, const float* slope,
-                     const float* step, const float* elev, float* out, float* slope_fp, float* step_fp, int sms, cudaStream_t s,
-                     int* launches);
+                     const float* step, const float* rough, const float* elev, float* out, float* slope_fp, float* step_fp,
+                     float* rough_fp, int sms, cudaStream_t s, int* launches);
 
 }  // namespace te

@@ -1076,7 +1076,15 @@ void make_fixup_args(const FusedState& st, const SlabView& v, const ChainDev& p,
   a.tip1 = w1.tips_on_circle; a.tip2 = w2.tips_on_circle;
   a.ncrit = p.ncrit;
   a.n_full = (double)wn.n;
+  a.n_full_i = wn.n;
   a.res = v.res; a.slope_crit = p.slope_crit; a.step_crit = p.step_crit; a.rough_crit = p.rough_crit;
+  a.inv_slope_crit = 1.0 / p.slope_crit; a.inv_rough_crit = 1.0 / p.rough_crit;
+  // Tier 2 rounds n_z to float32 itself unless n_z lies so close to a rounding boundary that the REFERENCE's own rounding errors
+  // could put its double result on the other side.  The reference forms the window offsets from absolute coordinates
+  // (X[a] - mean): relative error eps_off <= 4 * 2^-53 * |X|max / res; the small-angle term s = 1 - n_z <= 2e-4 inherits ~4 eps_off,
+  // i.e. 2e-4 * 16 * 2^-53 * (|X|max / res) / 2^-24 = 6e-12 * |X|max / res float32 ulps (6e-9 for the 8192^2 map at 0.02 m, with
+  // tier 2's own error on centred coordinates an order below).  The band is 100 times that, at least 1e-6 ulp.
+  a.nz_guard = std::max(1e-6, 100.0 * 6e-12 * v.coord_max / v.res);
   a.fuse_w = p.fuse_w;
   a.rowmask = (const unsigned char*)st.d_rowmask;
   a.colmask = (const unsigned char*)st.d_colmask;
@@ -1119,7 +1127,7 @@ int launch_chain_fused(FusedState& st, const SlabView& v, const ChainDev& p, int
   a.nmaps = nmaps;
   a.map_cells = (unsigned)((size_t)v.rows * v.out_ncols);
   plan_levels(a, v.out_ncols, nmaps, sms * WARPS_PER_CTA);
-  a.queue = count + 32;  // its own 128-byte line of the counter block
+  a.queue = count + 96;  // its own 128-byte line of the 512-byte counter block (words 8..49 hold tier-2 diagnostics)
   const double N = wn.n, K2 = wn.k2;
   a.a_cov = (float)(res * res * K2 / N);
   a.half_a = 0.5f * a.a_cov;

@@ -40,7 +40,10 @@ struct FixupArgs {
   int tip1, tip2;           // (+-2,0),(0,+-2) decided by the mask tables
   int ncrit;
   double n_full;            // cells of the full normals window
+  int n_full_i;
   double res, slope_crit, step_crit, rough_crit;
+  double inv_slope_crit, inv_rough_crit;
+  double nz_guard;          // half-width, in float32 ulps, of the band around a rounding boundary of n_z that tier 2 leaves to tier 3
   float fuse_w;
   const unsigned char* rowmask;
   const unsigned char* colmask;

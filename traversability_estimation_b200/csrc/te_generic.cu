@@ -38,9 +38,13 @@ __device__ __forceinline__ void for_circle(const SlabView& v, int i, int j, doub
   const int a0 = max(0, i - R), a1 = min(v.rows - 1, i + R);
   const int b0 = max(0, j - R), b1 = min(v.cols_total - 1, j + R);
   const double cx = v.X[i], cy = v.Y[j];
+  // not unrolled: a literal cell runs this loop nest a dozen times with different bodies, and the code of one cell is executed
+  // once — compact loops keep it inside the instruction cache (the tier-3 kernel is bound by instruction fetch otherwise)
+#pragma unroll 1
   for (int a = a0; a <= a1; ++a) {
     const double dx = v.X[a] - cx;
     const double dx2 = dx * dx;
+#pragma unroll 1
     for (int b = b0; b <= b1; ++b) {
       const double dy = v.Y[b] - cy;
       if (dx2 + dy * dy <= r2) f(a, b);

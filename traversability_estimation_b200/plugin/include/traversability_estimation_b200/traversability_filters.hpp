@@ -10,6 +10,17 @@
  * and one extra plugin for users who can edit the YAML:
  *   filters::FusedTraversabilityFilter<T>  = the whole chain of robot_filter_parameter.yaml:2-37 in one launch.
  * The shells hold no arithmetic: they marshal grid_map layers into the C ABI of include/te_b200.h.
+ *
+ * Fusion under the UNCHANGED YAML.  filters::FilterChain configures every filter before the first
+ * update(), so the three plugins register their parameters in a process-wide te_plugin::ChainRegistry at
+ * configure().  When exactly one SlopeFilter, one StepFilter and one RoughnessFilter are registered, the first of them whose
+ * update() sees a new `elevation` layer (keyed by geometry and a checksum of the layer) launches the whole fused chain once —
+ * te_chain(), normals included, regardless of what gridMapFilters/NormalVectorsFilter already wrote — and caches the three
+ * output layers in page-locked memory; the other two filters only emit their cached layer.  The normals radius is not visible to
+ * these plugins (it belongs to the third-party NormalVectorsFilter, robot_filter_parameter.yaml:8): the registry takes the
+ * RoughnessFilter's `estimation_radius` for it (equal in the shipped YAML; TE_B200_NORMALS_RADIUS overrides) and verifies the
+ * assumption on the first map by comparing its own surface_normal_z against the layer the upstream filter wrote; on a mismatch
+ * — or with TE_B200_FUSE_CHAIN=0 — every filter falls back to its stand-alone kernel, which reads the upstream normals.
  */
 #pragma once
 
@@ -35,11 +46,38 @@ class Device {
   ~Device();
   Device(const Device&) = delete;
   Device& operator=(const Device&) = delete;
-  te_ctx* get();  // nullptr + ROS_ERROR when no CUDA device can be opened
+  te_ctx* get();  // nullptr + ROS_ERROR when no CUDA device can be opened (device index: TE_B200_DEVICE, default 0)
 
  private:
   te_ctx* ctx_ = nullptr;
   bool failed_ = false;
+};
+
+// Process-wide registry behind the cross-plugin fusion described at the top of this file.
+class ChainRegistry {
+ public:
+  enum Kind { kSlope = 0, kStep = 1, kRoughness = 2 };
+  static ChainRegistry& instance();
+  // configure() / destructor of a plugin instance
+  void enroll(Kind kind, const void* owner);
+  void retire(Kind kind, const void* owner);
+  void setSlope(const void* owner, double critical);
+  void setStep(const void* owner, double critical, double r1, double r2, int cells);
+  void setRoughness(const void* owner, double critical, double radius);
+  // The cached output layer of `kind` for this map (unwrapped to the default start index, rows*cols floats, column-major), running
+  // the fused chain first when `elevation` is new.  nullptr: fusion is not available (not all three filters registered, disabled,
+  // no device, parameters the fused chain cannot take, or the upstream normals do not match) — the caller runs its own kernel.
+  const float* layer(Kind kind, const grid_map::GridMap& unwrapped_map);
+  // diagnostics for the tests: fused launches so far / layers served from the cache
+  long launches() const { return launches_; }
+  long served() const { return served_; }
+
+ private:
+  ChainRegistry();
+  ~ChainRegistry();
+  struct Impl;
+  Impl* impl_;
+  long launches_ = 0, served_ = 0;
 };
 
 }  // namespace te_plugin

@@ -2,7 +2,12 @@
 #include "traversability_estimation_b200/traversability_filters.hpp"
 
 #include <cmath>
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
 #include <limits>
+#include <mutex>
+#include <set>
 
 #if __has_include(<ros/console.h>)
 #include <ros/console.h>
@@ -19,7 +24,8 @@ Device::~Device() {
 }
 te_ctx* Device::get() {
   if (!ctx_ && !failed_) {
-    if (te_create(&ctx_, 0) != TE_OK) {
+    const char* dev = std::getenv("TE_B200_DEVICE");
+    if (te_create(&ctx_, dev ? std::atoi(dev) : 0) != TE_OK) {
       ROS_ERROR("libte_b200: %s", te_last_error());
       failed_ = true;
       ctx_ = nullptr;
@@ -83,17 +89,178 @@ te_chain_params yaml_defaults() {
 }
 
 }  // namespace
+
+// ------------------------------------------------------------------ ChainRegistry
+struct ChainRegistry::Impl {
+  std::mutex mu;
+  std::set<const void*> owners[3];   // configured instances per filter type: fusion needs exactly one of each
+  bool have[3] = {false, false, false};
+  te_chain_params params = yaml_defaults();
+  bool disabled = false;        // TE_B200_FUSE_CHAIN=0, or the upstream normals did not match ours
+  bool normals_checked = false;
+  Device device;
+  // cache: key + three layers in page-locked memory
+  te_geometry key_geo{};
+  uint64_t key_sum = 0;
+  bool valid = false;
+  size_t cap = 0;
+  float* out[4] = {nullptr, nullptr, nullptr, nullptr};   // slope, step, roughness, traversability (scratch)
+  float* nz = nullptr;                                    // first map only: our surface_normal_z (+ x, y scratch)
+  float* nxy[2] = {nullptr, nullptr};
+  ~Impl() {
+    for (float*& q : out) { te_host_free(q); q = nullptr; }
+    te_host_free(nz);
+    te_host_free(nxy[0]);
+    te_host_free(nxy[1]);
+  }
+};
+
+ChainRegistry::ChainRegistry() : impl_(new Impl) {
+  const char* e = std::getenv("TE_B200_FUSE_CHAIN");
+  if (e && std::atoi(e) == 0) impl_->disabled = true;
+}
+ChainRegistry::~ChainRegistry() { delete impl_; }
+ChainRegistry& ChainRegistry::instance() {
+  static ChainRegistry r;
+  return r;
+}
+void ChainRegistry::enroll(Kind k, const void* owner) {
+  std::lock_guard<std::mutex> lock(impl_->mu);
+  impl_->owners[k].insert(owner);   // a second instance of a type makes the chain ambiguous: no fusion while it lives
+  impl_->valid = false;
+}
+void ChainRegistry::retire(Kind k, const void* owner) {
+  std::lock_guard<std::mutex> lock(impl_->mu);
+  if (impl_->owners[k].erase(owner) && impl_->owners[k].empty()) impl_->have[k] = false;
+  impl_->valid = false;
+}
+void ChainRegistry::setSlope(const void* owner, double critical) {
+  enroll(kSlope, owner);
+  std::lock_guard<std::mutex> lock(impl_->mu);
+  impl_->params.slope_critical = critical;
+  impl_->have[kSlope] = true;
+}
+void ChainRegistry::setStep(const void* owner, double critical, double r1, double r2, int cells) {
+  enroll(kStep, owner);
+  std::lock_guard<std::mutex> lock(impl_->mu);
+  impl_->params.step_critical = critical;
+  impl_->params.step_first_radius = r1;
+  impl_->params.step_second_radius = r2;
+  impl_->params.step_critical_cells = cells;
+  impl_->have[kStep] = true;
+}
+void ChainRegistry::setRoughness(const void* owner, double critical, double radius) {
+  enroll(kRoughness, owner);
+  std::lock_guard<std::mutex> lock(impl_->mu);
+  impl_->params.roughness_critical = critical;
+  impl_->params.roughness_radius = radius;
+  const char* e = std::getenv("TE_B200_NORMALS_RADIUS");
+  impl_->params.normals_radius = e ? std::atof(e) : radius;   // see the header: not visible to these plugins
+  impl_->have[kRoughness] = true;
+}
+
+namespace {
+// Order-sensitive 64-bit checksum of a float layer (four independent lanes so that it runs at memory speed).
+uint64_t layer_checksum(const float* p, size_t n) {
+  uint64_t a = 0x9e3779b97f4a7c15ull, b = 0xc2b2ae3d27d4eb4full, c = 0x165667b19e3779f9ull, d = 0x27d4eb2f165667c5ull;
+  const uint32_t* w = reinterpret_cast<const uint32_t*>(p);
+  size_t i = 0;
+  for (; i + 4 <= n; i += 4) {
+    a = (a ^ w[i]) * 0x100000001b3ull;
+    b = (b ^ w[i + 1]) * 0x100000001b3ull;
+    c = (c ^ w[i + 2]) * 0x100000001b3ull;
+    d = (d ^ w[i + 3]) * 0x100000001b3ull;
+  }
+  for (; i < n; ++i) a = (a ^ w[i]) * 0x100000001b3ull;
+  return a ^ (b << 1 | b >> 63) ^ (c << 2 | c >> 62) ^ (d << 3 | d >> 61) ^ (uint64_t)n;
+}
+}  // namespace
+
+const float* ChainRegistry::layer(Kind kind, const grid_map::GridMap& m) {
+  Impl& I = *impl_;
+  std::lock_guard<std::mutex> lock(I.mu);
+  if (I.disabled) return nullptr;
+  for (int k = 0; k < 3; ++k)
+    if (I.owners[k].size() != 1 || !I.have[k]) return nullptr;
+  if (!m.exists("elevation")) return nullptr;   // the stand-alone path reports the missing layer the reference's way
+  const te_geometry g = geometry_of(m);
+  const size_t n = (size_t)g.rows * g.cols;
+  const float* elevation = m.get("elevation").data();
+  const uint64_t sum = layer_checksum(elevation, n);
+  if (I.valid && std::memcmp(&I.key_geo, &g, sizeof(g)) == 0 && I.key_sum == sum) {
+    ++served_;
+    return I.out[kind];
+  }
+  te_ctx* ctx = I.device.get();
+  if (!ctx) return nullptr;   // the caller's own kernel reports the failure
+  if (I.cap < n) {
+    for (float*& q : I.out) { te_host_free(q); q = nullptr; }
+    I.cap = 0;
+    for (float*& q : I.out)
+      if (te_host_alloc((void**)&q, n * sizeof(float)) != TE_OK) return nullptr;
+    I.cap = n;
+  }
+  I.valid = false;
+  const bool check = !I.normals_checked && m.exists("surface_normal_z");
+  if (check) {
+    te_host_free(I.nz); te_host_free(I.nxy[0]); te_host_free(I.nxy[1]);
+    I.nz = I.nxy[0] = I.nxy[1] = nullptr;
+    if (te_host_alloc((void**)&I.nz, n * sizeof(float)) != TE_OK || te_host_alloc((void**)&I.nxy[0], n * sizeof(float)) != TE_OK ||
+        te_host_alloc((void**)&I.nxy[1], n * sizeof(float)) != TE_OK)
+      return nullptr;
+  }
+  if (te_chain(ctx, &g, nullptr, &I.params, elevation, I.out[0], I.out[1], I.out[2], I.out[3], check ? I.nxy[0] : nullptr,
+               check ? I.nxy[1] : nullptr, check ? I.nz : nullptr, TE_MEM_HOST) != TE_OK) {
+    ROS_ERROR("fused chain: %s", te_last_error());
+    I.disabled = true;   // parameters the fused entry point rejects: the stand-alone kernels take over
+    return nullptr;
+  }
+  ++launches_;
+  if (check) {
+    // the upstream NormalVectorsFilter must have computed what the fused chain computes itself (same radius, same algorithm)
+    const float* theirs = m.get("surface_normal_z").data();
+    size_t bad = 0;
+    for (size_t i = 0; i < n; ++i) {
+      const float a = I.nz[i], b = theirs[i];
+      if (std::isnan(a) != std::isnan(b) || (!std::isnan(a) && std::fabs(a - b) > 1e-5f)) ++bad;
+    }
+    te_host_free(I.nz); te_host_free(I.nxy[0]); te_host_free(I.nxy[1]);
+    I.nz = I.nxy[0] = I.nxy[1] = nullptr;
+    I.normals_checked = true;
+    if (bad * 1000 > n) {   // more than 0.1 % of the cells: not rounding noise on degenerate windows
+      ROS_ERROR("libte_b200: surface normals of the upstream filter differ from the fused chain's in %zu of %zu cells "
+                "(radius %.4f assumed): cross-plugin fusion disabled, using the stand-alone kernels", bad, n, I.params.normals_radius);
+      I.disabled = true;
+      return nullptr;
+    }
+  }
+  I.key_geo = g;
+  I.key_sum = sum;
+  I.valid = true;
+  ++served_;
+  return I.out[kind];
+}
+
 }  // namespace te_plugin
 
 namespace filters {
 
 using te_plugin::geometry_of;
+using te_plugin::ChainRegistry;
+
+namespace {
+// Emit a cached (unwrapped) layer into `dst`, the layer's storage in the possibly circular-buffered output map.
+void emit(const grid_map::GridMap& like, bool wrapped, const float* cached, float* dst) {
+  if (wrapped) te_plugin::scatter_back(like, cached, dst);
+  else std::memcpy(dst, cached, sizeof(float) * (size_t)like.getSize()(0) * like.getSize()(1));
+}
+}  // namespace
 
 // ------------------------------------------------------------------ SlopeFilter
 template <typename T>
 SlopeFilter<T>::SlopeFilter() : criticalValue_(M_PI_4), type_("traversability_slope") {}
 template <typename T>
-SlopeFilter<T>::~SlopeFilter() {}
+SlopeFilter<T>::~SlopeFilter() { ChainRegistry::instance().retire(ChainRegistry::kSlope, this); }
 
 template <typename T>
 bool SlopeFilter<T>::configure() {
@@ -109,6 +276,7 @@ bool SlopeFilter<T>::configure() {
     ROS_ERROR("SlopeFilter did not find param map_type");
     return false;
   }
+  ChainRegistry::instance().setSlope(this, criticalValue_);
   return true;
 }
 
@@ -118,6 +286,10 @@ bool SlopeFilter<T>::update(const T& mapIn, T& mapOut) {
   mapOut.add(type_);  // NaN everywhere; cells without a surface normal keep it
   const te_plugin::Unwrapped u(mapOut);
   const float* nz = u.map().get("surface_normal_z").data();  // throws std::out_of_range like GridMap::at
+  if (const float* cached = ChainRegistry::instance().layer(ChainRegistry::kSlope, u.map())) {
+    emit(mapOut, u.wrapped, cached, mapOut.get(type_).data());
+    return true;
+  }
   te_ctx* ctx = device_.get();
   if (!ctx) return false;
   const te_geometry g = geometry_of(u.map());
@@ -137,7 +309,7 @@ template <typename T>
 StepFilter<T>::StepFilter()
     : criticalValue_(0.3), firstWindowRadius_(0.08), secondWindowRadius_(0.08), nCellCritical_(5), type_("traversability_step") {}
 template <typename T>
-StepFilter<T>::~StepFilter() {}
+StepFilter<T>::~StepFilter() { ChainRegistry::instance().retire(ChainRegistry::kStep, this); }
 
 template <typename T>
 bool StepFilter<T>::configure() {
@@ -177,6 +349,7 @@ bool StepFilter<T>::configure() {
     ROS_ERROR("Step filter did not find param map_type");
     return false;
   }
+  ChainRegistry::instance().setStep(this, criticalValue_, firstWindowRadius_, secondWindowRadius_, nCellCritical_);
   return true;
 }
 
@@ -186,6 +359,10 @@ bool StepFilter<T>::update(const T& mapIn, T& mapOut) {
   mapOut.add(type_);
   const te_plugin::Unwrapped u(mapOut);
   const float* elevation = u.map().get("elevation").data();
+  if (const float* cached = ChainRegistry::instance().layer(ChainRegistry::kStep, u.map())) {
+    emit(mapOut, u.wrapped, cached, mapOut.get(type_).data());
+    return true;
+  }
   te_ctx* ctx = device_.get();
   if (!ctx) return false;
   const te_geometry g = geometry_of(u.map());
@@ -209,7 +386,7 @@ bool StepFilter<T>::update(const T& mapIn, T& mapOut) {
 template <typename T>
 RoughnessFilter<T>::RoughnessFilter() : criticalValue_(0.3), estimationRadius_(0.3), type_("traversability_roughness") {}
 template <typename T>
-RoughnessFilter<T>::~RoughnessFilter() {}
+RoughnessFilter<T>::~RoughnessFilter() { ChainRegistry::instance().retire(ChainRegistry::kRoughness, this); }
 
 template <typename T>
 bool RoughnessFilter<T>::configure() {
@@ -233,6 +410,7 @@ bool RoughnessFilter<T>::configure() {
     ROS_ERROR("RoughnessFilter did not find param map_type");
     return false;
   }
+  ChainRegistry::instance().setRoughness(this, criticalValue_, estimationRadius_);
   return true;
 }
 
@@ -245,6 +423,10 @@ bool RoughnessFilter<T>::update(const T& mapIn, T& mapOut) {
   const float* elevation = u.map().get("elevation").data();
   const float* ny = u.map().get("surface_normal_y").data();
   const float* nz = u.map().get("surface_normal_z").data();
+  if (const float* cached = ChainRegistry::instance().layer(ChainRegistry::kRoughness, u.map())) {
+    emit(mapOut, u.wrapped, cached, mapOut.get(type_).data());
+    return true;
+  }
   te_ctx* ctx = device_.get();
   if (!ctx) return false;
   const te_geometry g = geometry_of(u.map());

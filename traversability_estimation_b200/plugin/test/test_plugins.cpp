@@ -15,6 +15,9 @@
 #include <pluginlib/class_list_macros.h>
 
 #include "te_b200.h"
+#include "traversability_estimation_b200/traversability_filters.hpp"
+
+#include <chrono>
 
 using Base = filters::FilterBase<grid_map::GridMap>;
 using Params = std::map<std::string, filters::ParamValue>;
@@ -153,6 +156,9 @@ static int test_chain(int argc, char** argv) {
     auto ft = create(kStep); ft->configure("stepFilter", step_yaml());
     auto fr = create(kRough); fr->configure("roughnessFilter", rough_yaml());
     if (!fs->update(m1, a) || !ft->update(a, b) || !fr->update(b, c)) { std::fprintf(stderr, "chain failed\n"); return 5; }
+    // cross-plugin fusion under the unchanged YAML: one fused launch, three layers served (0/0 with TE_B200_FUSE_CHAIN=0)
+    std::printf("REGISTRY launches=%ld served=%ld\n", te_plugin::ChainRegistry::instance().launches(),
+                te_plugin::ChainRegistry::instance().served());
     expect(!c.exists("step_height"), "StepFilter leaves no step_height layer behind");
     expect(c.exists("elevation") && c.exists("surface_normal_z"), "filters keep the other layers");
     dump(out + "_slope.bin", c.get("traversability_slope"));
@@ -172,11 +178,53 @@ static int test_chain(int argc, char** argv) {
   return g_fail;
 }
 
+// End-to-end time of the reference-named plugins exactly as filters::FilterChain drives them (host GridMaps in and out,
+// `mapOut = mapIn` deep copies included): slopeFilter -> stepFilter -> roughnessFilter on a map that already carries the
+// surface normals of the upstream NormalVectorsFilter.  One cell of the elevation changes per pass so every pass is a new map.
+static int test_bench(int argc, char** argv) {
+  if (argc < 6) { std::fprintf(stderr, "usage: bench R C res in.bin passes\n"); return 2; }
+  const int rows = std::atoi(argv[2]), cols = std::atoi(argv[3]);
+  const double res = std::atof(argv[4]);
+  const int passes = argc >= 7 ? std::atoi(argv[6]) : 5;
+  std::vector<float> elev((size_t)rows * cols);
+  FILE* f = std::fopen(argv[5], "rb");
+  if (!f || std::fread(elev.data(), sizeof(float), elev.size(), f) != elev.size()) { std::fprintf(stderr, "cannot read %s\n", argv[5]); return 3; }
+  std::fclose(f);
+  grid_map::GridMap m = make_map(rows, cols, res, 0.0, 0.0, elev);
+  for (const char* l : {"surface_normal_x", "surface_normal_y", "surface_normal_z"}) m.add(l);
+  te_ctx* ctx = nullptr;
+  if (te_create(&ctx, 0) != TE_OK) { std::fprintf(stderr, "%s\n", te_last_error()); return 4; }
+  te_geometry g{rows, cols, res, rows * res, cols * res, 0.0, 0.0, 0, 0};
+  te_chain_params p{};
+  p.normals_radius = 0.05; p.normals_algorithm = TE_NORMALS_FIXTURE; p.normals_positive_axis = 2; p.slope_critical = 1.0;
+  p.step_critical = 0.12; p.step_first_radius = 0.04; p.step_second_radius = 0.04; p.step_critical_cells = 4;
+  p.roughness_critical = 0.05; p.roughness_radius = 0.05; p.fuse_weight = 1.0f / 3.0f;
+  if (te_normals(ctx, &g, &p, m.get("elevation").data(), m.get("surface_normal_x").data(), m.get("surface_normal_y").data(),
+                 m.get("surface_normal_z").data(), TE_MEM_HOST) != TE_OK) { std::fprintf(stderr, "%s\n", te_last_error()); return 4; }
+  te_destroy(ctx);
+  auto fs = create(kSlope); fs->configure("slopeFilter", slope_yaml());
+  auto ft = create(kStep); ft->configure("stepFilter", step_yaml());
+  auto fr = create(kRough); fr->configure("roughnessFilter", rough_yaml());
+  double best = 1e30, total = 0.0;
+  for (int it = -1; it < passes; ++it) {   // pass -1 warms up (context creation, page-locked cache, normals check)
+    m.get("elevation")(0, 0) = elev[0] + 1e-4f * (float)(it + 2);
+    grid_map::GridMap a, b, c;
+    const auto t0 = std::chrono::steady_clock::now();
+    if (!fs->update(m, a) || !ft->update(a, b) || !fr->update(b, c)) { std::fprintf(stderr, "chain failed\n"); return 5; }
+    const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    if (it >= 0) { best = std::min(best, ms); total += ms; }
+  }
+  std::printf("PLUGIN_CHAIN rows=%d cols=%d passes=%d mean_ms=%.3f best_ms=%.3f launches=%ld served=%ld\n", rows, cols, passes,
+              total / passes, best, te_plugin::ChainRegistry::instance().launches(), te_plugin::ChainRegistry::instance().served());
+  return 0;
+}
+
 int main(int argc, char** argv) {
-  if (argc < 2) { std::fprintf(stderr, "usage: test_plugins configure|nogpu|chain ...\n"); return 2; }
+  if (argc < 2) { std::fprintf(stderr, "usage: test_plugins configure|nogpu|chain|bench ...\n"); return 2; }
   const std::string mode = argv[1];
   if (mode == "configure") return test_configure();
   if (mode == "nogpu") return test_nogpu();
   if (mode == "chain") return test_chain(argc, argv);
+  if (mode == "bench") return test_bench(argc, argv);
   return 2;
 }

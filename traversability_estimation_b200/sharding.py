@@ -59,3 +59,42 @@ def exchange_halo(dist, buf, plan: SlabPlan, halo: int):
         ops.append(dist.P2POp(dist.irecv, buf[hl + n:hl + n + hr], plan.rank + 1))
     for w in dist.batch_isend_irecv(ops):
         w.wait()
+
+
+class PeerHalo:
+    """Peer-mapped halo exchange of one slab buffer through the C ABI (te_halo_pull): every rank exports its buffer and a
+    "layer ready" event once (CUDA IPC), opens its neighbours', and from then on a halo exchange is two asynchronous
+    device-to-device copies straight out of the neighbours' buffers over NVLink, queued on the context stream.
+    torch.distributed only carries the 64-byte handles at set-up."""
+
+    def __init__(self, dist, ctx, te, buf, plan: SlabPlan):
+        self.ctx, self.te, self.plan, self.buf = ctx, te, plan, buf
+        self.slab = te.Slab(plan.col_begin, plan.col_count, plan.halo_left, plan.halo_right)
+        self.ready, ev_handle = ctx.event_create_ipc()
+        mine = {"mem": ctx.ipc_export(buf.data_ptr()), "ev": ev_handle,
+                "slab": (plan.col_begin, plan.col_count, plan.halo_left, plan.halo_right)}
+        everyone = [None] * plan.world
+        dist.all_gather_object(everyone, mine)
+        self._opened = []
+        self.left = self._open(everyone[plan.rank - 1]) if plan.rank > 0 else None
+        self.right = self._open(everyone[plan.rank + 1]) if plan.rank < plan.world - 1 else None
+
+    def _open(self, info):
+        ptr = self.ctx.ipc_open(info["mem"])
+        ev = self.ctx.event_open_ipc(info["ev"])
+        self._opened.append((ptr, ev))
+        return self.te.HaloPeer(ptr, self.te.Slab(*info["slab"]), ev)
+
+    def publish(self):
+        """This rank's owned columns are valid (as far as the context stream is concerned)."""
+        self.ctx.event_record(self.ready)
+
+    def pull(self, g):
+        self.ctx.halo_pull(g, self.slab, self.buf, self.left, self.right)
+
+    def close(self):
+        for ptr, ev in self._opened:
+            self.ctx.event_destroy(ev)
+            self.ctx.ipc_close(ptr)
+        self._opened = []
+        self.ctx.event_destroy(self.ready)
