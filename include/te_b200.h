@@ -188,6 +188,21 @@ int te_footprint2(te_ctx* ctx, const te_geometry* g, const te_slab* slab, const 
                   const float* elevation, float* traversability_footprint, float* slope_footprint_or_null,
                   float* step_footprint_or_null, float* roughness_footprint_or_null, int memory);
 
+/* TraversabilityMap::checkFootprintPath for circular footprints — checkCircularFootprintPath, TraversabilityMap.cpp:345-462 —
+ * for a BATCH of paths in one launch (one thread per path: the service callback of the reference checks one path per call;
+ * planners and MPC roll-outs ask for hundreds).  It is evaluated on a complete traversability_footprint layer, i.e. the output
+ * of te_footprint(radius, offset) for the radius of the paths: every isTraversable(center, radius + offset, ...) of the reference
+ * then takes its memoised branch (:667-673: traversability = layer value, traversable iff value != 0), a centre outside the map the
+ * default branch (:660-666).  Path q is the poses poses_xy[2*path_begin[q] .. 2*path_begin[q+1]) (x, y in the map frame); for a
+ * path of one pose the circle at the pose is checked (:365-390), otherwise every fourth cell (nSkip = 3, :401) of the grid line
+ * between consecutive poses, and the segment means are combined weighted by segment length (:437-449).  Outputs per path:
+ * TraversabilityResult.is_safe and .traversability (0 when unsafe); .area is 0 for circular footprints.  Not covered:
+ * checkRobotInclination_ (:359, :386), the untraversable polygon, publishing.  Poses of a multi-pose path must lie inside the map
+ * (the reference does not check getIndex's return value there): such a path is reported unsafe. */
+int te_check_footprint_paths(te_ctx* ctx, const te_geometry* g, const float* traversability_footprint,
+                             double traversability_default, int32_t npaths, const int32_t* path_begin, const double* poses_xy,
+                             uint8_t* is_safe, double* traversability, int memory);
+
 /* ---- Multi-GPU: one map tiled into column slabs, one process (rank) per GPU -------------------------------
  * The chain and the footprint sweep are stencils of fixed radius, so the only exchange step is a one-shot copy of the
  * neighbours' boundary columns of the INPUT layer(s) into this rank's halo.  The reference has no counterpart (it is a

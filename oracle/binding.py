@@ -160,6 +160,22 @@ def footprint(g, fp, traversability, slope_l, step_l, elevation, nthreads=0, rou
     return out, sfp, stfp, rfp
 
 
+def check_circular_paths(g, footprint_layer, traversability_default, path_begin, poses_xy):
+    """(is_safe uint8[npaths], traversability float64[npaths]) of TraversabilityMap::checkCircularFootprintPath per path."""
+    f = _layer(g, footprint_layer)
+    pb = np.ascontiguousarray(path_begin, dtype=np.int32)
+    xy = np.ascontiguousarray(poses_xy, dtype=np.float64)
+    n = len(pb) - 1
+    safe = np.zeros(n, dtype=np.uint8)
+    trav = np.zeros(n, dtype=np.float64)
+    L = lib()
+    L.teo_check_circular_paths.argtypes = [C.POINTER(Geometry), C.c_void_p, C.c_double, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    rc = L.teo_check_circular_paths(C.byref(g), f.ctypes.data, traversability_default, n, pb.ctypes.data, xy.ctypes.data,
+                                    safe.ctypes.data, trav.ctypes.data)
+    assert rc == 0, rc
+    return safe, trav
+
+
 def spiral_offsets(radius, resolution):
     cap = int((2 * np.ceil(radius / resolution) + 3) ** 2)
     di = np.empty(cap, dtype=np.int32)

@@ -94,6 +94,13 @@ int teo_footprint2(const teo_geometry* g, const teo_footprint_params* p, const f
                    const float* slope, const float* step, const float* roughness_or_null, const float* elevation,
                    float* out_footprint, float* slope_fp_or_null, float* step_fp_or_null, float* rough_fp_or_null, int nthreads);
 
+/* TraversabilityMap::checkCircularFootprintPath (TraversabilityMap.cpp:345-462) for a batch of paths on a
+ * traversability_footprint layer that is valid everywhere (memoised isTraversable branch :667-673): path q is the poses
+ * poses_xy[2*path_begin[q] .. 2*path_begin[q+1]).  Outputs TraversabilityResult.is_safe / .traversability per path. */
+int teo_check_circular_paths(const teo_geometry* g, const float* traversability_footprint, double traversability_default,
+                             int npaths, const int32_t* path_begin, const double* poses_xy, uint8_t* is_safe,
+                             double* traversability);
+
 /* Visit order of grid_map::SpiralIterator for a centre far from the map border: writes up to `cap`
  * (di,dj) pairs, returns the number of cells visited.  radius/resolution in metres. */
 int teo_spiral_offsets(double radius, double resolution, int32_t* di, int32_t* dj, int cap);

@@ -360,4 +360,78 @@ int teo_footprint2(const teo_geometry* g, const teo_footprint_params* p, const f
   return 0;
 }
 
+// TraversabilityMap::checkCircularFootprintPath, TraversabilityMap.cpp:345-462, for a batch of paths, evaluated on a
+// traversability_footprint layer that is valid everywhere (i.e. after traversabilityFootprint(radius, offset), :307-318): every
+// isTraversable(center, ...) then takes the memoised branch :667-673 (traversability = layer value, traversable = value != 0);
+// centres outside the map take :660-666 (traversability = default).  checkRobotInclination_ (:359,:386) is off, no polygons.
+// Deviation noted: `lengthPath` (:441) is an uninitialised block-scope local in the reference; the intended running path
+// length is used here.
+int teo_check_circular_paths(const teo_geometry* g, const float* footprint, double traversability_default, int npaths,
+                             const int32_t* path_begin, const double* poses_xy, uint8_t* is_safe, double* traversability) {
+  if (!g || g->rows <= 0 || g->cols <= 0 || !footprint || npaths < 0 || !path_begin || !poses_xy || !is_safe || !traversability) return 1;
+  Map m{g->rows, g->cols, g->resolution, {g->length_x, g->length_y}, {g->position_x, g->position_y}, nullptr, nullptr, nullptr, nullptr, {}, {}};
+  m.X.resize(m.rows);
+  m.Y.resize(m.cols);
+  for (int i = 0; i < m.rows; ++i) m.X[i] = cell_coord(m.pos.x, m.len.x, m.res, i);
+  for (int j = 0; j < m.cols; ++j) m.Y[j] = cell_coord(m.pos.y, m.len.y, m.res, j);
+  auto circle = [&](V2 c, double& t) -> bool {  // isTraversable(center, ...) on the memoised layer
+    int i, j;
+    if (!is_inside(m, c) || !get_index(m, c, i, j)) {                       // :660-666
+      t = traversability_default;
+      return traversability_default != 0.0;
+    }
+    t = (double)footprint[(size_t)j * m.rows + i];                          // :668
+    return t != 0.0;                                                         // :669
+  };
+  for (int q = 0; q < npaths; ++q) {
+    const int b = path_begin[q], n = path_begin[q + 1] - b;
+    is_safe[q] = 0;                                                          // :352-353
+    traversability[q] = 0.0;
+    if (n <= 0) continue;                                                    // :330-334
+    double result = 0.0, lengthPath = 0.0;
+    bool ok = true;
+    V2 start{0.0, 0.0}, end{0.0, 0.0};
+    for (int k = 0; k < n && ok; ++k) {
+      start = end;                                                           // :361
+      end = V2{poses_xy[2 * (b + k)], poses_xy[2 * (b + k) + 1]};            // :362-363
+      if (n == 1) {                                                          // :365
+        double t;
+        if (!circle(end, t)) { ok = false; break; }                          // :371-388
+        result = t;                                                          // :389
+      }
+      if (n > 1 && k > 0) {                                                  // :392
+        int si, sj, ei, ej;
+        if (!get_index(m, start, si, sj) || !get_index(m, end, ei, ej)) { ok = false; break; }  // poses must lie in the map
+        double sum = 0.0;
+        int nLine = 0, visit = 0;
+        bool trav = true;
+        for_line(ei, ej, si, sj, [&](int a, int c2) {                        // :406 LineIterator(endIndex, startIndex)
+          if ((visit++ & 3) != 0) return true;                               // :424-428: three cells skipped after every check
+          double t;
+          trav = trav && circle(V2{m.X[a], m.Y[c2]}, t);                     // :407-410
+          if (!trav) return false;                                           // :416-419
+          sum += t;                                                          // :421
+          ++nLine;                                                           // :422
+          return true;
+        });
+        if (!trav) { ok = false; break; }                                    // :450-453
+        const double t = sum / (double)nLine;                                // :438
+        const double lengthSegment = std::sqrt((end.x - start.x) * (end.x - start.x) + (end.y - start.y) * (end.y - start.y));  // :440
+        if (k > 1) {                                                         // :441-445
+          const double lengthPreviousPath = lengthPath;
+          lengthPath += lengthSegment;
+          result = (lengthSegment * t + lengthPreviousPath * result) / lengthPath;
+        } else {
+          lengthPath = lengthSegment;                                        // :446-448
+          result = t;
+        }
+      }
+    }
+    if (!ok) continue;
+    is_safe[q] = 1;                                                          // :458
+    traversability[q] = result;
+  }
+  return 0;
+}
+
 }  // extern "C"

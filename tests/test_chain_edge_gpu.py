@@ -113,6 +113,7 @@ def test_fused_against_literal_kernel_at_scale(te, ctx):
     import bench
     rows = cols = 4096
     z = bench.terrain_torch(torch, rows, 0, cols, cols, 11, 0.01, torch.device("cuda"))
+    torch.cuda.synchronize()   # the context runs on its own stream: the input must be complete
     g = te.Geometry.make(rows, cols, 0.02)
     p = te.ChainParams.yaml_defaults(0)
     ctx.set_stream(None)
@@ -134,3 +135,28 @@ def test_fused_against_literal_kernel_at_scale(te, ctx):
         worst[k] = (bad, float((d / tol).max()))
         assert bad == 0, (k, bad, float(d.max()))
     print(worst)
+
+
+def test_streaming_slope_filter_is_bit_identical_to_the_literal_expression(te, ctx):
+    """te_slope streams (certified polynomial acos, fp64 fallback on rounding boundaries): every float32 of the layer must equal
+    float32(acos(double(nz)) < crit ? 1 - acos/crit : 0), the reference's expression (SlopeFilter.cpp:74-81), including exact 0/1,
+    NaN, negative and out-of-range normals, and the neighbourhood of the branch point."""
+    import torch
+    n = 1 << 22
+    gen = torch.Generator().manual_seed(5)
+    nz = torch.rand(n, generator=gen, dtype=torch.float64)
+    nz[: n // 4] = 1.0 - nz[: n // 4] ** 4 * 1e-3                 # near-flat normals, where acos is ill-conditioned
+    nz = nz.to(torch.float32)
+    nz[0:8] = torch.tensor([1.0, 0.0, -1.0, -0.25, float("nan"), 1.5, float("inf"), 0.5403023], dtype=torch.float32)  # cos(1.0) ~ branch point
+    g = te.Geometry.make(2048, n // 2048, 0.02)
+    for crit in (1.0, 0.7853981633974483, 0.3):
+        ref = torch.acos(nz.double())
+        ref = torch.where(ref < crit, 1.0 - ref / crit, torch.zeros_like(ref)).to(torch.float32)
+        ref[~torch.isfinite(nz)] = float("nan")
+        d_in, d_out = nz.cuda(), torch.empty(n, dtype=torch.float32, device="cuda")
+        ctx.slope(g, crit, d_in, d_out, te.MEM_DEVICE)
+        ctx.synchronize()
+        got = d_out.cpu()
+        same = (got.view(torch.int32) == ref.view(torch.int32)) | (torch.isnan(got) & torch.isnan(ref))
+        # torch's acos on the CPU and CUDA's libdevice acos may differ in the last bit of the double: allow a handful of cells
+        assert int((~same).sum()) <= 4, (crit, int((~same).sum()), got[~same][:5], ref[~same][:5])

@@ -129,10 +129,17 @@ def test_footprint_with_roughness_verification(te, ctx, oracle):
     (TraversabilityMap.cpp:779-783, 895-921).  A rough terrain makes zero-roughness-traversability patches that block cells the
     slope/step checks let through."""
     rows, cols = 200, 180
-    z = synth.terrain(rows, cols, 0.02, 61, "rough")
-    z[60:110, 40:100] = synth.terrain(50, 60, 0.02, 62, "gentle")     # a smooth island in rough ground
+    z = synth.terrain(rows, cols, 0.02, 61, "mixed")
     og, g = oracle.Geometry.make(rows, cols, 0.02), te.Geometry.make(rows, cols, 0.02)
     ch = oracle.chain(og, oracle.ChainParams.yaml_defaults(0), z)
+    # a terrain whose roughness layer hits 0 is blocked by its step layer long before (3 cm of noise already saturates the step
+    # filter), so the roughness layer of this test is synthetic: the chain's own layer with patches of zeros of several sizes
+    rng = np.random.default_rng(61)
+    rough = ch["roughness"].copy()
+    for _ in range(60):
+        a, b, h, w = int(rng.integers(0, rows - 12)), int(rng.integers(0, cols - 12)), int(rng.integers(1, 12)), int(rng.integers(1, 12))
+        rough[a:a + h, b:b + w] = 0.0
+    ch["roughness"] = rough
     assert (ch["roughness"] == 0).sum() > 500
     fo, ft = oracle.FootprintParams.yaml_defaults(), te.FootprintParams.yaml_defaults()
     t, s, st, r, e = (np.asfortranarray(x, dtype=np.float32) for x in (ch["traversability"], ch["slope"], ch["step"], ch["roughness"], z))
@@ -154,3 +161,29 @@ def test_footprint_with_roughness_verification(te, ctx, oracle):
     with pytest.raises(te.TEError) as err:   # the flag without the layer: TE_ERR_MISSING_LAYER, like GridMap::at on a missing layer
         ctx.footprint(g, ft, t, s, st, e, out, te.MEM_HOST)
     assert err.value.code == -2
+
+
+def test_batched_circular_footprint_paths(te, ctx, oracle):
+    """§8(f)-2: checkCircularFootprintPath (TraversabilityMap.cpp:345-462) for a batch of paths on the footprint layer."""
+    rows, cols = 256, 240
+    z = synth.terrain(rows, cols, 0.02, 91, "mixed")
+    og, g = oracle.Geometry.make(rows, cols, 0.02), te.Geometry.make(rows, cols, 0.02)
+    ch = oracle.chain(og, oracle.ChainParams.yaml_defaults(0), z)
+    fo = oracle.FootprintParams.yaml_defaults()
+    fpl, _, _ = oracle.footprint(og, fo, ch["traversability"], ch["slope"], ch["step"], z)
+    rng = np.random.default_rng(7)
+    lx, ly = rows * 0.02, cols * 0.02
+    begin, poses = [0], []
+    for q in range(400):
+        n = int(rng.integers(0, 7)) if q > 3 else (0, 1, 2, 5)[q]      # empty, single-pose and multi-pose paths
+        p = rng.uniform([-0.48 * lx, -0.48 * ly], [0.48 * lx, 0.48 * ly], size=(n, 2))
+        if q % 50 == 7 and n > 0:
+            p[0] = [0.6 * lx, 0.0]                                       # a pose outside the map
+        poses.extend(p.tolist())
+        begin.append(len(poses))
+    poses = np.asarray(poses, dtype=np.float64).reshape(-1, 2)
+    ref_safe, ref_t = oracle.check_circular_paths(og, fpl, fo.traversability_default, begin, poses)
+    safe, t = ctx.check_footprint_paths(g, fpl, fo.traversability_default, begin, poses)
+    assert np.array_equal(safe, ref_safe)
+    assert np.array_equal(t, ref_t)                                     # same double arithmetic, bit for bit
+    assert 10 < int(safe.sum()) < 390 and safe[0] == 0                   # safe and unsafe paths both occur; the empty path is unsafe

@@ -67,6 +67,7 @@ def test_config3_8192_against_oracle_and_eight_slabs(te, ctx, oracle):
     import bench
     n = 8192
     z = bench.terrain_torch(torch, n, 0, n, n, 11, 0.01, torch.device("cuda"))  # (cols, rows) on the device
+    torch.cuda.synchronize()   # the context runs on its own stream: the input must be complete
     g, p = te.Geometry.make(n, n, 0.02), te.ChainParams.yaml_defaults(0)
     outs = [torch.empty((n, n), dtype=torch.float32, device="cuda") for _ in range(4)]
     ctx.set_stream(None)

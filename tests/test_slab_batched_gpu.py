@@ -63,6 +63,7 @@ def test_size_independent_properties_at_scale(te, ctx):
     import bench
     rows = cols = 4096
     z = bench.terrain_torch(torch, rows, 0, cols, cols, 7, 0.01, torch.device("cuda"))
+    torch.cuda.synchronize()   # the context runs on its own stream: the input must be complete
     g = te.Geometry.make(rows, cols, 0.02)
     p = te.ChainParams.yaml_defaults(0)
     ctx.set_stream(None)
@@ -97,6 +98,7 @@ def test_pipelined_host_path_equals_device_path(te, ctx):
     import bench
     rows, cols = 2048, 2304
     z = bench.terrain_torch(torch, rows, 0, cols, cols, 9, 0.01, torch.device("cuda"))
+    torch.cuda.synchronize()   # the context runs on its own stream: the input must be complete
     g = te.Geometry.make(rows, cols, 0.02)
     p = te.ChainParams.yaml_defaults(0)
     ctx.set_stream(None)

@@ -3,6 +3,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import sys
 import subprocess
 
 import numpy as np
@@ -17,7 +18,7 @@ KERNEL_AUTO, KERNEL_GENERIC, KERNEL_FUSED = 0, 1, 2
 
 EXPORTS = ["te_create", "te_destroy", "te_last_error", "te_abi_version", "te_set_stream", "te_synchronize",
            "te_set_kernel", "te_get_stats", "te_enable_timing", "te_get_timing", "te_get_flag_counters", "te_get_escalation_stats", "te_fused_plan", "te_slope", "te_normals", "te_step", "te_roughness", "te_chain",
-           "te_chain_batched", "te_footprint", "te_footprint2", "te_ipc_export", "te_ipc_open", "te_ipc_close", "te_event_create_ipc", "te_event_open_ipc",
+           "te_chain_batched", "te_footprint", "te_footprint2", "te_check_footprint_paths", "te_ipc_export", "te_ipc_open", "te_ipc_close", "te_event_create_ipc", "te_event_open_ipc",
            "te_event_record", "te_event_destroy", "te_halo_pull", "te_host_alloc", "te_host_free"]
 
 
@@ -166,6 +167,16 @@ class Context:
         h = C.c_void_p()
         self._check(self._L.te_create(C.byref(h), device))
         self._h = h
+        self._own_stream = True   # device-memory calls run on the context's own (non-blocking) stream until set_stream(ptr)
+
+    def _order_after_torch(self, memory):
+        """This ctypes view is used with torch tensors as device memory.  While the context runs on its own stream nothing orders
+        its kernels after the torch kernels that produce their inputs: drain torch's current stream first (callers that pass
+        their stream with set_stream need no such thing, nor does the C ABI itself — ordering is the caller's there)."""
+        if memory == MEM_DEVICE and self._own_stream and "torch" in sys.modules:
+            torch = sys.modules["torch"]
+            if torch.cuda.is_available():
+                torch.cuda.current_stream().synchronize()
 
     def _check(self, rc):
         if rc != 0:
@@ -184,6 +195,7 @@ class Context:
 
     def set_stream(self, stream_ptr):
         self._check(self._L.te_set_stream(self._h, stream_ptr))
+        self._own_stream = not stream_ptr
 
     def synchronize(self):
         self._check(self._L.te_synchronize(self._h))
@@ -219,29 +231,36 @@ class Context:
         return list(a), list(b)
 
     def slope(self, g, critical, nz, out, memory):
+        self._order_after_torch(memory)
         self._check(self._L.te_slope(self._h, C.byref(g), critical, _addr(nz), _addr(out), memory))
 
     def normals(self, g, p, elevation, nx, ny, nz, memory):
+        self._order_after_torch(memory)
         self._check(self._L.te_normals(self._h, C.byref(g), C.byref(p), _addr(elevation), _addr(nx), _addr(ny), _addr(nz), memory))
 
     def step(self, g, p, elevation, out, memory):
+        self._order_after_torch(memory)
         self._check(self._L.te_step(self._h, C.byref(g), C.byref(p), _addr(elevation), _addr(out), memory))
 
     def roughness(self, g, p, elevation, nx, ny, nz, out, memory):
+        self._order_after_torch(memory)
         self._check(self._L.te_roughness(self._h, C.byref(g), C.byref(p), _addr(elevation), _addr(nx), _addr(ny), _addr(nz),
                                          _addr(out), memory))
 
     def chain(self, g, p, elevation, slope, step, roughness, traversability, memory, slab=None, nx=None, ny=None, nz=None):
+        self._order_after_torch(memory)
         self._check(self._L.te_chain(self._h, C.byref(g), C.byref(slab) if slab is not None else None, C.byref(p),
                                      _addr(elevation), _addr(slope), _addr(step), _addr(roughness), _addr(traversability),
                                      _addr(nx), _addr(ny), _addr(nz), memory))
 
     def chain_batched(self, g, p, nmaps, elevation, slope, step, roughness, traversability, memory):
+        self._order_after_torch(memory)
         self._check(self._L.te_chain_batched(self._h, C.byref(g), C.byref(p), nmaps, _addr(elevation), _addr(slope),
                                              _addr(step), _addr(roughness), _addr(traversability), memory))
 
     def footprint(self, g, fp, traversability, slope, step, elevation, out, memory, slab=None, slope_fp=None, step_fp=None,
                   roughness=None, roughness_fp=None):
+        self._order_after_torch(memory)
         if roughness is None and roughness_fp is None:
             self._check(self._L.te_footprint(self._h, C.byref(g), C.byref(slab) if slab is not None else None, C.byref(fp),
                                              _addr(traversability), _addr(slope), _addr(step), _addr(elevation), _addr(out),
@@ -250,6 +269,19 @@ class Context:
             self._check(self._L.te_footprint2(self._h, C.byref(g), C.byref(slab) if slab is not None else None, C.byref(fp),
                                               _addr(traversability), _addr(slope), _addr(step), _addr(roughness), _addr(elevation),
                                               _addr(out), _addr(slope_fp), _addr(step_fp), _addr(roughness_fp), memory))
+
+    def check_footprint_paths(self, g, footprint_layer, traversability_default, path_begin, poses_xy):
+        """Host convenience: (is_safe uint8[npaths], traversability float64[npaths]); footprint_layer is a column-major host layer."""
+        f = np.asfortranarray(footprint_layer, dtype=np.float32)
+        pb = np.ascontiguousarray(path_begin, dtype=np.int32)
+        xy = np.ascontiguousarray(poses_xy, dtype=np.float64)
+        n = len(pb) - 1
+        safe, trav = np.zeros(n, dtype=np.uint8), np.zeros(n, dtype=np.float64)
+        self._L.te_check_footprint_paths.argtypes = [C.c_void_p, C.POINTER(Geometry), C.c_void_p, C.c_double, C.c_int32, C.c_void_p,
+                                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        self._check(self._L.te_check_footprint_paths(self._h, C.byref(g), f.ctypes.data, traversability_default, n, pb.ctypes.data,
+                                                     xy.ctypes.data, safe.ctypes.data, trav.ctypes.data, MEM_HOST))
+        return safe, trav
 
     # ---- multi-GPU halo (te_halo_pull and the IPC helpers around it)
     def ipc_export(self, device_ptr) -> bytes:
@@ -283,6 +315,7 @@ class Context:
         self._check(self._L.te_event_destroy(event))
 
     def halo_pull(self, g, slab, layer, left=None, right=None):
+        self._order_after_torch(MEM_DEVICE)
         self._check(self._L.te_halo_pull(self._h, C.byref(g), C.byref(slab), _addr(layer),
                                          C.byref(left) if left is not None else None, C.byref(right) if right is not None else None))
 

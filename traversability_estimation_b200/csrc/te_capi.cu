@@ -802,6 +802,41 @@ int te_footprint(te_ctx* c, const te_geometry* g, const te_slab* slab, const te_
   return te_footprint2(c, g, slab, p, trav, slope, step, nullptr, elev, out, slope_fp, step_fp, nullptr, memory);
 }
 
+int te_check_footprint_paths(te_ctx* c, const te_geometry* g, const float* footprint, double traversability_default, int32_t npaths,
+                             const int32_t* path_begin, const double* poses_xy, uint8_t* is_safe, double* traversability, int memory) {
+  TE_ENTER(c);
+  if (int rc = check_geometry(g)) return rc;
+  if (!footprint) return fail(TE_ERR_MISSING_LAYER, "layer traversability_footprint is missing");
+  if (npaths < 0 || !path_begin || !poses_xy || !is_safe || !traversability) return fail(TE_ERR_BAD_ARG, "null argument or negative path count");
+  if (npaths == 0) return TE_OK;
+  if (int rc = ensure_geometry(c, g)) return rc;
+  const te_slab s{0, g->cols, 0, 0};
+  const te::SlabView v = make_view(c, g, s);
+  if (memory == TE_MEM_DEVICE) {
+    te::launch_check_paths(v, g, traversability_default, footprint, npaths, path_begin, poses_xy, is_safe, traversability, c->stream);
+    return launch_check(c, "k_check_paths");
+  }
+  // host arguments: path_begin is readable here, so the pose count is known
+  const int32_t nposes = path_begin[npaths];
+  if (nposes < 0) return fail(TE_ERR_BAD_ARG, "path_begin must be non-decreasing");
+  const size_t lbytes = sizeof(float) * (size_t)g->rows * g->cols;
+  TE_CUDA(c->stage[0].reserve(lbytes));
+  TE_CUDA(c->stage[1].reserve(sizeof(int32_t) * (size_t)(npaths + 1)));
+  TE_CUDA(c->stage[2].reserve(sizeof(double) * 2 * (size_t)std::max(nposes, 1)));
+  TE_CUDA(c->stage[4].reserve((size_t)npaths));
+  TE_CUDA(c->stage[5].reserve(sizeof(double) * (size_t)npaths));
+  TE_CUDA(cudaMemcpyAsync(c->stage[0].p, footprint, lbytes, cudaMemcpyHostToDevice, c->stream));
+  TE_CUDA(cudaMemcpyAsync(c->stage[1].p, path_begin, sizeof(int32_t) * (size_t)(npaths + 1), cudaMemcpyHostToDevice, c->stream));
+  TE_CUDA(cudaMemcpyAsync(c->stage[2].p, poses_xy, sizeof(double) * 2 * (size_t)nposes, cudaMemcpyHostToDevice, c->stream));
+  te::launch_check_paths(v, g, traversability_default, (const float*)c->stage[0].p, npaths, (const int*)c->stage[1].p,
+                         (const double*)c->stage[2].p, (unsigned char*)c->stage[4].p, (double*)c->stage[5].p, c->stream);
+  if (int rc = launch_check(c, "k_check_paths")) return rc;
+  TE_CUDA(cudaMemcpyAsync(is_safe, c->stage[4].p, (size_t)npaths, cudaMemcpyDeviceToHost, c->stream));
+  TE_CUDA(cudaMemcpyAsync(traversability, c->stage[5].p, sizeof(double) * (size_t)npaths, cudaMemcpyDeviceToHost, c->stream));
+  TE_CUDA(cudaStreamSynchronize(c->stream));
+  return TE_OK;
+}
+
 // A te IPC handle is the CUDA handle of the ALLOCATION that contains the pointer (cudaIpcGetMemHandle always describes the whole
 // allocation; sub-allocating pools such as torch's caching allocator hand out interior pointers) plus the offset into it.
 struct TeIpcHandle {

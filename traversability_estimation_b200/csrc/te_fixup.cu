@@ -279,7 +279,7 @@ __device__ bool normals_t2(const FixupArgs& A, const Elev& E, int i, int j, floa
   return true;
 }
 
-__global__ void __launch_bounds__(128, 6) k_fixup_t2(FixupArgs A, const float* __restrict__ elev, ChainOut o,
+__global__ void __launch_bounds__(128, 8) k_fixup_t2(FixupArgs A, const float* __restrict__ elev, ChainOut o,
                                                   const unsigned* __restrict__ list, const unsigned* __restrict__ count,
                                                   unsigned cap, unsigned* list3, unsigned* count3, unsigned cap3) {
   unsigned n = *count;

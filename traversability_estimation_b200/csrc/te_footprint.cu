@@ -54,6 +54,10 @@ struct FpArgs {
   int words;                  // words per column
   const unsigned char* near;  // per input-buffer cell: distance (rows) to the nearest blocked cell of its column, 255 = none within 31
   signed char halfw_c[64];    // copy of `halfw` in the kernel parameters (constant bank)
+  // full-disk sum without a blocked cell in sight (the common case): element offsets into the prefix sums, relative to the
+  // centre's own entry P[column j][row i], of the two ends of disk column l (index l + L), and the running cell count
+  int off_hi[64], off_lo[64];
+  short cntp[65];
 };
 
 __device__ __forceinline__ float lay(const FpArgs& A, const float* l, int i, int j) {  // caller guarantees (i,j) is in the map
@@ -224,13 +228,50 @@ __device__ bool check_step_d(const FpArgs& A, const Layers& L, int i, int j) {
   return true;
 }
 
-// blocked[] covers the whole input buffer (columns in_col0 .. in_col0+in_ncols).
-__global__ void __launch_bounds__(128) k_predicates(FpArgs A, Layers L, unsigned char* __restrict__ blocked, float* slope_fp, float* step_fp,
-                                                    float* rough_fp) {
-  const long long total = (long long)A.rows * A.in_ncols;
-  for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < total; c += (long long)gridDim.x * blockDim.x) {
-    const int i = (int)(c % A.rows);
-    const int j = A.in_col0 + (int)(c / A.rows);
+// isTraversableForFilters for every cell of the input buffer (columns in_col0 .. in_col0+in_ncols), in two steps.  Almost every
+// cell passes trivially — checkForSlope / checkForStep / checkForRoughness return true at once unless the cell's own layer
+// value is exactly 0 (TraversabilityMap.cpp:869, :796, :897) — so k_pred_classify settles those with two or three coalesced
+// loads and collects the others on a work list, which k_pred_heavy walks with one thread per listed cell (the window count,
+// the submap / gap walk): the heavy threads are no longer scattered one or two per warp over the whole map.
+__global__ void __launch_bounds__(256) k_pred_classify(FpArgs A, Layers L, unsigned char* __restrict__ blocked, float* slope_fp,
+                                                       float* step_fp, float* rough_fp, unsigned* __restrict__ list,
+                                                       unsigned* __restrict__ count) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lb = blockIdx.y;
+  const bool in = i < A.rows;
+  bool heavy = false;
+  size_t c = 0;
+  if (in) {
+    c = (size_t)lb * A.rows + i;
+    heavy = __ldg(L.slope + c) == 0.0f || __ldg(L.step + c) == 0.0f || (A.verify_rough && __ldg(L.rough + c) == 0.0f);
+    if (!heavy) {
+      blocked[c] = 0;
+      const int oj = lb + A.in_col0 - A.out_col0;
+      if (oj >= 0 && oj < A.out_ncols) {
+        const size_t oc = (size_t)oj * A.rows + i;
+        if (slope_fp) slope_fp[oc] = nanf_();
+        if (step_fp) step_fp[oc] = nanf_();
+        if (rough_fp) rough_fp[oc] = nanf_();
+      }
+    }
+  }
+  const unsigned m = __ballot_sync(0xffffffffu, heavy);
+  if (m) {
+    const int lane = threadIdx.x & 31;
+    unsigned base = 0;
+    if (lane == 0) base = atomicAdd(count, (unsigned)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (heavy) list[base + __popc(m & ((1u << lane) - 1u))] = (unsigned)c;
+  }
+}
+
+__global__ void __launch_bounds__(128) k_pred_heavy(FpArgs A, Layers L, unsigned char* __restrict__ blocked, float* slope_fp, float* step_fp,
+                                                    float* rough_fp, const unsigned* __restrict__ list, const unsigned* __restrict__ count) {
+  const unsigned n = *count;
+  for (unsigned k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+    const unsigned c = list[k];
+    const int i = (int)(c % (unsigned)A.rows);
+    const int j = A.in_col0 + (int)(c / (unsigned)A.rows);
     const bool s_ok = check_slope_d(A, L, i, j);
     bool t_ok = true;
     float sfp = nanf_(), tfp = nanf_();
@@ -366,32 +407,51 @@ __global__ void __launch_bounds__(256) k_fp_nearest(FpArgs A, unsigned char* __r
 // and "sum / count of the visited cells" are 2L+1 column queries instead of ~pi r^2 visits; only when a blocker
 // exists is the ring that holds the first one walked in SpiralIterator order.
 __global__ void __launch_bounds__(256) k_sweep_fast(FpArgs A, Layers L, const unsigned char* __restrict__ blocked, float* __restrict__ out) {
-  const long long total = (long long)A.rows * A.out_ncols;
   const int W = 2 * A.L + 1;
-  for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < total; c += (long long)gridDim.x * blockDim.x) {
-    const int i = (int)(c % A.rows);
-    const int j = A.out_col0 + (int)(c / A.rows);
-    const double cx = A.X[i], cy = A.Y[j];
-    // ---- nearest blocked cell of the visited set, as a squared index distance ------------------------
-    int best = 0x7fffffff;
+  // one block = 256 consecutive rows of ONE output column (blockIdx.y): a warp's centres share their column, so everything that
+  // depends only on the column — which disk columns exist, whether any blocked cell lies near the warp at all — is warp-uniform
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = A.out_col0 + (int)blockIdx.y;
+  {
+    const int lane = threadIdx.x & 31, i0 = i - lane;
+    if (i0 >= A.rows) return;  // whole warp beyond the last row
+    const bool active = i < A.rows;
+    const size_t c = (size_t)blockIdx.y * A.rows + (active ? i : 0);
+    const double cx = A.X[active ? i : 0], cy = A.Y[j];
     // disk columns that exist in the map and in this slab's buffer
     const int l_lo = max(-A.L, max(-j, A.in_col0 - j)), l_hi = min(A.L, min(A.cols_total - 1 - j, A.in_col0 + A.in_ncols - 1 - j));
+    // ---- warp-wide early out: is any cell blocked in the box of rows [i0 - L, i0 + 31 + L] x disk columns?  (packed flags,
+    //      a few words per column, shared by the 32 centres)  Mostly not: then no lane has anything to look for.
+    bool warp_any;
     {
+      const int w0 = max(i0 - A.L, 0) >> 5, w1 = min(i0 + 31 + A.L, A.rows - 1) >> 5, nw = w1 - w0 + 1;
+      const int ne = (l_hi - l_lo + 1) * nw;
+      unsigned acc = 0;
+      for (int e = lane; e < ne; e += 32) {
+        const int l = l_lo + e / nw, w = w0 + e % nw;
+        acc |= __ldg(A.bits + (size_t)(j + l - A.in_col0) * A.words + w);
+      }
+      warp_any = __any_sync(0xffffffffu, acc != 0u);
+    }
+    if (!active) return;
+    // ---- nearest blocked cell of the visited set, as a squared index distance ------------------------
+    int best = 0x7fffffff;
+    if (warp_any) {
       const unsigned char* nr = A.near + (size_t)(j + l_lo - A.in_col0) * A.rows + i;
       for (int l = l_lo; l <= l_hi; ++l, nr += A.rows) {
         const int g = (int)__ldg(nr);              // nearest blocked row offset in this column
         const int hw = A.halfw_c[l + A.L];
         if (g <= hw) best = min(best, g * g + l * l);
       }
-    }
-    for (int q = 0; q < A.n_fuzzy; ++q) {
-      const int w = A.fuzzy[q];
-      const int di = (int)(signed char)(w & 0xff), dj = (int)(signed char)((w >> 8) & 0xff);
-      const int a = i + di, b = j + dj, lb = b - A.in_col0;
-      if (a < 0 || b < 0 || a >= A.rows || b >= A.cols_total || lb < 0 || lb >= A.in_ncols) continue;
-      const double dx = A.X[a] - cx, dy = A.Y[b] - cy;
-      if (!(dx * dx + dy * dy <= A.rmax2)) continue;
-      if (blocked[(size_t)lb * A.rows + a]) best = min(best, di * di + dj * dj);
+      for (int q = 0; q < A.n_fuzzy; ++q) {
+        const int w = A.fuzzy[q];
+        const int di = (int)(signed char)(w & 0xff), dj = (int)(signed char)((w >> 8) & 0xff);
+        const int a = i + di, b = j + dj, lb = b - A.in_col0;
+        if (a < 0 || b < 0 || a >= A.rows || b >= A.cols_total || lb < 0 || lb >= A.in_ncols) continue;
+        const double dx = A.X[a] - cx, dy = A.Y[b] - cy;
+        if (!(dx * dx + dy * dy <= A.rmax2)) continue;
+        if (blocked[(size_t)lb * A.rows + a]) best = min(best, di * di + dj * dj);
+      }
     }
     // ---- sums over the visited cells before the first blocked one --------------------------------------
     const bool any = best != 0x7fffffff;
@@ -399,7 +459,20 @@ __global__ void __launch_bounds__(256) k_sweep_fast(FpArgs A, Layers L, const un
     const signed char* hwt = any ? (A.inner + (size_t)dstar * W) : A.halfw;
     double t = 0.0, t_b = 0.0;
     int n = 0;
-    {
+    if (!warp_any && i - A.L >= 0 && i + A.L < A.rows) {
+      // nothing blocked near this warp and no clipping along the rows: 2 loads and 2 additions per disk column, offsets from
+      // the constant bank
+      const double* pc0 = A.P + (size_t)(j - A.in_col0) * ((size_t)A.rows + 1) + i;
+      int l = l_lo + A.L;
+      const int l_end = l_hi + A.L;
+      for (; l + 1 <= l_end; l += 2) {
+        t += pc0[A.off_hi[l]] - pc0[A.off_lo[l]];
+        t_b += pc0[A.off_hi[l + 1]] - pc0[A.off_lo[l + 1]];
+      }
+      if (l <= l_end) t += pc0[A.off_hi[l]] - pc0[A.off_lo[l]];
+      t += t_b;
+      n = (int)A.cntp[l_end + 1] - (int)A.cntp[l_lo + A.L];
+    } else {
       const double* pc = A.P + (size_t)(j + l_lo - A.in_col0) * (A.rows + 1);
       const size_t pstride = (size_t)A.rows + 1;
       if (i - A.L >= 0 && i + A.L < A.rows) {  // no clipping along the rows: two independent accumulators
@@ -473,6 +546,76 @@ __global__ void __launch_bounds__(256) k_sweep_fast(FpArgs A, Layers L, const un
   }
 }
 
+// TraversabilityMap::checkCircularFootprintPath (TraversabilityMap.cpp:345-462) for a batch of paths — one thread per path — on a
+// traversability_footprint layer that is valid everywhere: every isTraversable(center, ...) takes the memoised branch
+// (:667-673), centres outside the map the default branch (:660-666).  No inclination check, no polygons.
+__global__ void __launch_bounds__(128) k_check_paths(FpArgs A, const float* __restrict__ fp, int npaths, const int* __restrict__ path_begin,
+                                                     const double* __restrict__ xy, unsigned char* __restrict__ is_safe,
+                                                     double* __restrict__ trav_out) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= npaths) return;
+  const int b = path_begin[q], n = path_begin[q + 1] - b;
+  is_safe[q] = 0;
+  trav_out[q] = 0.0;
+  if (n <= 0) return;
+  auto circle = [&](double cx, double cy, double& t) -> bool {
+    int i, j;
+    if (!is_inside_d(A, cx, cy) || !get_index_d(A, cx, cy, i, j)) {
+      t = A.tdefault;
+      return A.tdefault != 0.0;
+    }
+    t = (double)lay(A, fp, i, j);
+    return t != 0.0;
+  };
+  double result = 0.0, lengthPath = 0.0;
+  double sx = 0.0, sy = 0.0, ex = 0.0, ey = 0.0;
+  for (int k = 0; k < n; ++k) {
+    sx = ex; sy = ey;
+    ex = xy[2 * (b + k)]; ey = xy[2 * (b + k) + 1];
+    if (n == 1) {
+      double t;
+      if (!circle(ex, ey, t)) return;
+      result = t;
+    }
+    if (n > 1 && k > 0) {
+      int si, sj, ei, ej;
+      if (!get_index_d(A, sx, sy, si, sj) || !get_index_d(A, ex, ey, ei, ej)) return;
+      // LineIterator (Bresenham) from the end index to the start index, every fourth cell checked
+      const int dx = abs(si - ei), dy = abs(sj - ej);
+      int i1x = (si >= ei) ? 1 : -1, i2x = i1x, i1y = (sj >= ej) ? 1 : -1, i2y = i1y;
+      int den, num, numAdd, nCells;
+      if (dx >= dy) { i1x = 0; i2y = 0; den = dx; num = dx / 2; numAdd = dy; nCells = dx + 1; }
+      else { i2x = 0; i1y = 0; den = dy; num = dy / 2; numAdd = dx; nCells = dy + 1; }
+      int li = ei, lj = ej, nLine = 0;
+      double sum = 0.0;
+      for (int c = 0; c < nCells; ++c) {
+        if ((c & 3) == 0) {
+          double t;
+          if (!circle(A.X[li], A.Y[lj], t)) return;
+          sum += t;
+          ++nLine;
+        }
+        num += numAdd;
+        if (num >= den) { num -= den; li += i1x; lj += i1y; }
+        li += i2x; lj += i2y;
+      }
+      const double t = sum / (double)nLine;
+      const double lx = ex - sx, ly = ey - sy;
+      const double lengthSegment = sqrt(lx * lx + ly * ly);
+      if (k > 1) {
+        const double lengthPreviousPath = lengthPath;
+        lengthPath += lengthSegment;
+        result = (lengthSegment * t + lengthPreviousPath * result) / lengthPath;
+      } else {
+        lengthPath = lengthSegment;
+        result = t;
+      }
+    }
+  }
+  is_safe[q] = 1;
+  trav_out[q] = result;
+}
+
 inline int signum(int v) { return (0 < v) - (v < 0); }
 
 // grid_map::SpiralIterator::generateRing, executed literally.
@@ -503,10 +646,22 @@ void FootprintState::release() {
   if (d_block) cudaFree(d_block);
   if (d_tables) cudaFree(d_tables);
   if (d_prefix) cudaFree(d_prefix);
-  d_spiral = d_block = d_tables = d_prefix = nullptr;
-  spiral_cap = block_cap = tables_cap = prefix_cap = 0;
+  if (d_list) cudaFree(d_list);
+  d_spiral = d_block = d_tables = d_prefix = d_list = nullptr;
+  spiral_cap = block_cap = tables_cap = prefix_cap = list_cap = 0;
   tables_valid = false;
   valid = false;
+}
+
+void launch_check_paths(const SlabView& v, const te_geometry* g, double traversability_default, const float* footprint, int npaths,
+                        const int* path_begin, const double* xy, unsigned char* is_safe, double* trav, cudaStream_t s) {
+  FpArgs a{};
+  a.rows = v.rows; a.cols_total = v.cols_total; a.in_col0 = v.in_col0; a.in_ncols = v.in_ncols;
+  a.out_col0 = v.out_col0; a.out_ncols = v.out_ncols;
+  a.res = g->resolution; a.lenx = g->length_x; a.leny = g->length_y; a.posx = g->position_x; a.posy = g->position_y;
+  a.X = v.X; a.Y = v.Y;
+  a.tdefault = traversability_default;
+  k_check_paths<<<(npaths + 127) / 128, 128, 0, s>>>(a, footprint, npaths, path_begin, xy, is_safe, trav);
 }
 
 int footprint_halo(const te_geometry* g, const te_footprint_params* p) {
@@ -564,12 +719,26 @@ int launch_footprint(FootprintState& st, const SlabView& v, const te_geometry* g
   const long long t1 = (long long)ncell_in, t2 = (long long)v.rows * v.out_ncols;
   const int g1 = (int)std::min<long long>((t1 + 127) / 128, (long long)sms * 16);
   const int g2 = (int)std::min<long long>((t2 + 255) / 256, (long long)sms * 8);
-  k_predicates<<<std::max(g1, 1), 128, 0, s>>>(a, L, (unsigned char*)st.d_block, slope_fp, step_fp, rough_fp);
+  {
+    if (ncell_in >= ((size_t)1 << 32)) { st.why = "slab of 2^32 or more cells"; return TE_ERR_UNSUPPORTED; }
+    if (st.list_cap < ncell_in + 1) {
+      if (st.d_list) cudaFree(st.d_list);
+      st.d_list = nullptr; st.list_cap = 0;
+      if (cudaMalloc(&st.d_list, sizeof(unsigned) * (ncell_in + 1)) != cudaSuccess) { st.why = "cudaMalloc(predicate work list) failed"; return TE_ERR_CUDA; }
+      st.list_cap = ncell_in + 1;
+    }
+    unsigned* cnt = (unsigned*)st.d_list;          // word 0: list length; entries follow
+    unsigned* lst = cnt + 1;
+    cudaMemsetAsync(cnt, 0, sizeof(unsigned), s);
+    const dim3 gc((unsigned)((v.rows + 255) / 256), (unsigned)v.in_ncols);
+    k_pred_classify<<<gc, 256, 0, s>>>(a, L, (unsigned char*)st.d_block, slope_fp, step_fp, rough_fp, lst, cnt);
+    k_pred_heavy<<<std::max(g1, 1), 128, 0, s>>>(a, L, (unsigned char*)st.d_block, slope_fp, step_fp, rough_fp, lst, cnt);
+  }
   const int Lmax = (int)std::floor(rmax / g->resolution + 1e-9);
-  const bool fast = Lmax <= 31 && std::getenv("TE_FOOTPRINT_BRUTE") == nullptr;
+  const bool fast = Lmax <= 31 && v.out_ncols <= 65535 && std::getenv("TE_FOOTPRINT_BRUTE") == nullptr;
   if (!fast) {
     k_sweep<<<std::max(g2, 1), 256, 0, s>>>(a, L, (const unsigned char*)st.d_block, out);
-    if (launches) *launches = 2;
+    if (launches) *launches = 3;
     return 0;
   }
   // ---- prefix-sum sweep: tables (cached with the spiral) + per-call prefix/bit arrays -----------------
@@ -650,12 +819,22 @@ int launch_footprint(FootprintState& st, const SlabView& v, const te_geometry* g
   a.bits = (const unsigned*)((char*)st.d_prefix + pbytes);
   a.near = (const unsigned char*)st.d_prefix + pbytes + wbytes;
   std::memcpy(a.halfw_c, st.h_halfw, sizeof(a.halfw_c));
+  {
+    const int pstride = v.rows + 1;
+    a.cntp[0] = 0;
+    for (int k = 0; k < 64; ++k) {
+      const int l = k - st.L, h = (k <= 2 * st.L) ? (int)st.h_halfw[k] : -1;
+      a.off_hi[k] = h >= 0 ? l * pstride + h + 1 : 0;
+      a.off_lo[k] = h >= 0 ? l * pstride - h : 0;   // a column outside the disk contributes P[0] - P[0]
+      a.cntp[k + 1] = (short)(a.cntp[k] + (h >= 0 ? 2 * h + 1 : 0));
+    }
+  }
   const int g3 = std::min(sms * 8, (v.in_ncols + 7) / 8);
   const int g1b = (int)std::min<long long>((t1 + 255) / 256, (long long)sms * 8);
   k_fp_prepare<<<std::max(g3, 1), 256, 0, s>>>(a, L, (const unsigned char*)st.d_block, (double*)st.d_prefix, (unsigned*)((char*)st.d_prefix + pbytes));
   k_fp_nearest<<<std::max(g1b, 1), 256, 0, s>>>(a, (unsigned char*)st.d_prefix + pbytes + wbytes);
-  k_sweep_fast<<<std::max(g2, 1), 256, 0, s>>>(a, L, (const unsigned char*)st.d_block, out);
-  if (launches) *launches = 4;
+  k_sweep_fast<<<dim3((unsigned)((v.rows + 255) / 256), (unsigned)v.out_ncols), 256, 0, s>>>(a, L, (const unsigned char*)st.d_block, out);
+  if (launches) *launches = 5;
   return 0;
 }
 

@@ -27,6 +27,8 @@ struct FootprintState {
   signed char h_halfw[64] = {0};
   void* d_prefix = nullptr;
   size_t prefix_cap = 0;
+  void* d_list = nullptr;    // work list of the cells whose predicates need the window / gap-walk code (word 0: length)
+  size_t list_cap = 0;
   void invalidate() { valid = false; tables_valid = false; }
   void release();
 };
@@ -37,5 +39,9 @@ int launch_footprint(FootprintState& st, const SlabView& v, const te_geometry* g
                      const std::vector<double>& X, const std::vector<double>& Y, const float* trav, const float* slope,
                      const float* step, const float* rough, const float* elev, float* out, float* slope_fp, float* step_fp,
                      float* rough_fp, int sms, cudaStream_t s, int* launches);
+
+// TraversabilityMap::checkCircularFootprintPath for a batch of paths on a complete traversability_footprint layer (device pointers).
+void launch_check_paths(const SlabView& v, const te_geometry* g, double traversability_default, const float* footprint, int npaths,
+                        const int* path_begin, const double* xy, unsigned char* is_safe, double* trav, cudaStream_t s);
 
 }  // namespace te
