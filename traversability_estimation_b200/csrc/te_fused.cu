@@ -43,7 +43,10 @@ constexpr int EROWS = SROWS + 4;   // staged elevation rows (2 more each side fo
 constexpr int CH = 5;              // columns per TMA chunk = unroll factor = ring depth
 constexpr int NST = 4;             // TMA ring stages per warp
 constexpr int STAGE_BYTES = 1408;  // EROWS*CH*4 = 1360, padded so every stage is 128-byte aligned
-constexpr int SHBUF_BYTES = 288;   // 2 pad + 64 + 2 pad floats, padded
+constexpr int SHBUF_BYTES = 272;   // 2 pad + 64 + 2 pad floats (264 bytes), 16-byte aligned
+constexpr int NSHB = 3;            // step_height exchange buffers: buffer PH % 3, so the address is a compile-time offset, consecutive
+                                   // steps never share a buffer and a buffer is rewritten two steps (= one __syncwarp) after it was read
+constexpr int STAGE_PAD = EROWS * CH * 4;  // first byte of a stage TMA does not write: 5 x 4 column-mask bytes of the chunk live there
 // TE_SMEM_RINGS=1 (default): the run-sum and column-statistics rings live in shared memory instead of registers (one
 // 8-byte element per lane and slot: conflict-free), which brings the kernel to 154 registers — under the 168 that a third
 // warp per scheduler needs (the register file is four 16 K partitions) — so 12 warps fit per SM (TE_WPC=12 TE_REGS=168).
@@ -67,11 +70,14 @@ constexpr bool STRAIGHT = TE_STRAIGHT != 0;
 constexpr unsigned RING_REG1 = TE_RING_REG1;
 enum RingId { R_A1, R_B1, R_Q1, R_A2, R_B2, R_Q2, R_C1MN, R_C1MX, R_S3MX, R_S3C, NRING };
 constexpr int RING_BYTES = SMEM_RINGS ? NRING * 5 * 32 * 8 : 0;
-constexpr int WARP_SMEM_BYTES = NST * STAGE_BYTES + 2 * SHBUF_BYTES + 64 + RING_BYTES;  // 6272 = 49 * 128 (+ 12800 = 100 * 128)
+constexpr int WARP_SMEM_BYTES = NST * STAGE_BYTES + (NSHB * SHBUF_BYTES + 48 + 127) / 128 * 128 + RING_BYTES;  // 5632 + 896 (+ 12800): 151 * 128; 12 warps = 226.5 KB
 #ifndef TE_WPC
 #define TE_WPC 12
 #endif
 constexpr int WARPS_PER_CTA = TE_WPC;
+static_assert(WARPS_PER_CTA * WARP_SMEM_BYTES <= 232448, "the warps of a CTA must fit the 227 KB of dynamic shared memory");
+constexpr int WARP_AUX_OFF = NST * STAGE_BYTES + NSHB * SHBUF_BYTES;  // mbarriers (NST x 8 bytes), then the work-list cursor (8 bytes)
+constexpr int WARP_RING_OFF = WARP_SMEM_BYTES - RING_BYTES;
 #ifdef TE_REGS
 #define TE_KERNEL_ATTR __maxnreg__(TE_REGS)
 #else
@@ -170,6 +176,15 @@ __device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) {
 }
 __device__ __forceinline__ f2 bc(float v) { return mk(v, v); }
 __device__ __forceinline__ f2 neg2(f2 a) { return a ^ 0x8000000080000000ull; }
+// -a for both rows, written as two scalar negations: ptxas folds the pair into the operand modifier of the consuming
+// FFMA2/FADD2/FMUL2 (`FFMA2 R4, -R4.F32x2.HI_LO, ...`), so the negation costs no instruction (an integer XOR would cost two).
+__device__ __forceinline__ f2 negf2(f2 a) { return mk(-lo(a), -hi(a)); }
+// TE_NOCORR: bit mask of the Newton corrections that are dropped (bit0 D = sqrt(hh): MUFU.SQRT, rel. error 2^-23; bit1 g2/dph and
+// bit2 g2/m^2: MUFU.RCP, 2^-23).  What they feed tolerates it: lambda0 is certified against 1e-5 cmag, s = 1 - n_z against a
+// relative error budget of >= 2e-6, theta = atan(g/m) moves by sin(theta) cos(theta) eps.
+#ifndef TE_NOCORR
+#define TE_NOCORR 7
+#endif
 
 // Three-input min/max (FMNMX3) with IEEE minNum/maxNum semantics: NaN operands are skipped, which is
 // exactly how the reference's step filter treats invalid cells (StepFilter.cpp:126,159); the result is
@@ -366,19 +381,27 @@ __device__ __forceinline__ float min2n(float a, float b) {
 __device__ __forceinline__ Normal2 finish_normal2(const FusedArgs& A, f2 Sw, f2 Sk, f2 Sl, f2 Sww, f2 ec) {
   Normal2 o;
   const f2 mw = mul2(Sw, A.k_invN);
-  const f2 c = fma2(mul2(Sw, A.k_minvN), mw, mul2(Sww, A.k_invN));  // Czz = Sww/N - (Sw/N)^2
+  const f2 c = fma2(negf2(mw), mw, mul2(Sww, A.k_invN));  // Czz = Sww/N - (Sw/N)^2
   const f2 p = mul2(Sk, A.k_kp), q = mul2(Sl, A.k_kp);               // Cxz, Cyz
   const f2 g2 = fma2(p, p, mul2(q, q));
-  const f2 h = fma2(c, A.k_mhalf, A.k_half_a);                        // (a - c)/2
+  const f2 h = fma2(negf2(c), A.k_half, A.k_half_a);                  // (a - c)/2
   const f2 hh = fma2(h, h, g2);
+#if TE_NOCORR & 1
+  const f2 D = mk(sqrt_a(lo(hh)), sqrt_a(hi(hh)));
+#else
   const f2 rD = mk(rsq_a(lo(hh)), rsq_a(hi(hh)));
   const f2 D0 = mul2(hh, rD);
-  const f2 D = fma2(fma2(mul2(D0, A.k_mone), D0, hh), mul2(rD, A.k_half), D0);  // sqrt(hh), one correction
+  const f2 D = fma2(fma2(negf2(D0), D0, hh), mul2(rD, A.k_half), D0);  // sqrt(hh), one correction
+#endif
   const float h0 = lo(h), h1 = hi(h);
   const f2 dph = add2(D, mk(fabsf(h0), fabsf(h1)));
   const f2 rq = mk(rcp_a(lo(dph)), rcp_a(hi(dph)));
+#if TE_NOCORR & 2
+  const f2 qq = mul2(g2, rq);
+#else
   const f2 q0 = mul2(g2, rq);
-  const f2 qq = fma2(fma2(mul2(q0, A.k_mone), dph, g2), rq, q0);  // g2 / dph, one correction
+  const f2 qq = fma2(fma2(negf2(q0), dph, g2), rq, q0);  // g2 / dph, one correction
+#endif
   const bool hx = h0 >= 0.f, hy = h1 >= 0.f;
   const f2 m = mk(hx ? lo(dph) : lo(qq), hy ? hi(dph) : hi(qq));  // a - lambda0
   const f2 cmag = mk(hx ? lo(c) : A.a_cov, hy ? hi(c) : A.a_cov);
@@ -386,20 +409,24 @@ __device__ __forceinline__ Normal2 finish_normal2(const FusedArgs& A, f2 Sw, f2 
   const f2 m2 = mul2(m, m);
   const f2 nn = add2(m2, g2);
   const f2 r0 = mk(rsq_a(lo(nn)), rsq_a(hi(nn)));
-  const f2 rn = mul2(r0, fma2(mul2(mul2(nn, A.k_mhalf), r0), r0, A.k_1p5));  // rsqrt(nn), one Newton step
-  const f2 nrn = mul2(rn, A.k_mone);
-  o.nx = mul2(p, nrn);
-  o.ny = mul2(q, nrn);
+  const f2 rn = mul2(r0, fma2(negf2(mul2(mul2(nn, A.k_half), r0)), r0, A.k_1p5));  // rsqrt(nn), one Newton step
+  o.nx = mul2(negf2(p), rn);
+  o.ny = mul2(negf2(q), rn);
   const f2 nzg = mul2(m, rn);
   // roughness = sqrt(lambda0 * N/(N-1)); lambda0 is a difference of two terms of size cmag
   const f2 rr2 = mul2(lam0, A.k_nnm1);
   const f2 r = mk(sqrt_a(fmaxf(lo(rr2), 0.f)), sqrt_a(fmaxf(hi(rr2), 0.f)));
   const f2 thr = mul2(mul2(cmag, cmag), A.k_rough_thr);
   // small inclination: n_z = 1 - s with s from t = tan^2(theta) (series; exact rounding of 1 - s)
+#if TE_NOCORR & 4
+  // t is used only where h >= 0 (smx/smy), and there m = dph: g2 / m^2 = (g2 / dph) / dph with the reciprocal already at hand
+  const f2 t = mul2(mul2(g2, rq), rq);
+#else
   const f2 rm = mk(rcp_a(lo(m2)), rcp_a(hi(m2)));
   const f2 t0 = mul2(g2, rm);
-  const f2 t = fma2(fma2(mul2(t0, A.k_mone), m2, g2), rm, t0);
-  const f2 s = mul2(t, fma2(mul2(t, A.k_mone), fma2(t, A.k_m03125, A.k_0375), A.k_half));
+  const f2 t = fma2(fma2(negf2(t0), m2, g2), rm, t0);
+#endif
+  const f2 s = mul2(t, fma2(negf2(t), fma2(t, A.k_m03125, A.k_0375), A.k_half));
   const f2 nzs = sub2(A.k_one, s);
   const bool smx = hx && lo(t) < 2.5e-3f, smy = hy && hi(t) < 2.5e-3f;
   const f2 nz = mk(fminf(smx ? lo(nzs) : lo(nzg), 1.0f), fminf(smy ? hi(nzs) : hi(nzg), 1.0f));
@@ -495,9 +522,23 @@ __device__ __noinline__ void store_normals(float* pnx, float* pny, float* pnz, b
   *reinterpret_cast<f2*>(pnz + oc) = nz;
 }
 
+// Column tips of a chunk (CH march steps; column `cb` arrives at phase 0).  Lane ph < CH writes the word of phase ph into the
+// padding of the chunk's TMA stage: byte 0/1 = pass-1 tips (0,-2)/(0,+2) of column js = cb + ph - 2, byte 2/3 = pass-2 tips of
+// column jo = cb + ph - 4; 0x00 where the on-circle offset belongs to the window (colmask bit set), 0xff where it does not.
+__device__ __forceinline__ void fill_colmask(const FusedArgs& A, unsigned stage_addr, int cb, int lane) {
+  if (lane < CH) {
+    const int js = cb + lane - 2, jo = js - 2;
+    const unsigned x = (js >= 0 && js < A.cols_total) ? A.colmask[js] : 0u;
+    const unsigned y = (jo >= 0 && jo < A.cols_total) ? A.colmask[jo] : 0u;
+    const unsigned w = ((x & 1u) ? 0u : 0xffu) | ((x & 2u) ? 0u : 0xff00u) | ((y & 4u) ? 0u : 0xff0000u) | ((y & 8u) ? 0u : 0xff000000u);
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(stage_addr + STAGE_PAD + lane * 4), "r"(w) : "memory");
+  }
+}
+
 template <class S>
 struct StepCtx {
   const FusedArgs& A;
+  unsigned e_base;    // shared address of stage 0 of the warp's TMA ring
   unsigned e_lane;    // shared address of the lane's first staged row in stage 0 / column 0
   unsigned sh_lane;   // shared address of the lane's first step_height row in buffer 0
   int lane;
@@ -505,6 +546,7 @@ struct StepCtx {
   int q0, q1;         // output columns of the unit
   f2 tipU1, tipD1;    // pass-1 row tips: +0.0 where the on-circle offset (-2,0)/(+2,0) belongs to the window, NaN where not
   f2 tipU2, tipD2;    // same for pass 2
+  f2 cntU2, cntD2;    // pass-2 row tips as count weights: 1.0 where the offset belongs to the window, 0.0 where not
   f2* rg;             // SMEM_RINGS: the lane's element of ring 0 / slot 0 in shared memory (rings are 32 lanes x 8 bytes apart)
   unsigned lstate;    // shared address of the warp's work-list cursor {chunk base, entries used}
   bool out_ok;        // lane produces output rows (lanes 1..30 and inside the map)
@@ -515,7 +557,7 @@ struct StepCtx {
 
 // One march step: column ce = q0 - 4 + t arrives.  PH = t % 5.
 template <class S, int PH, bool KN>
-__device__ __forceinline__ void march_step(StepCtx<S>& C, Lane<S>& L, int t, unsigned stage, unsigned cm_js, unsigned cm_jo) {
+__device__ __forceinline__ void march_step(StepCtx<S>& C, Lane<S>& L, int t, unsigned stage) {
   const FusedArgs& A = C.A;
   constexpr int S0 = PH, S1 = (PH + 4) % 5, S2 = (PH + 3) % 5, S3 = (PH + 2) % 5, S4 = (PH + 1) % 5;  // slot of age 0..4
   const int ce = C.q0 - 4 + t;
@@ -574,7 +616,11 @@ __device__ __forceinline__ void march_step(StepCtx<S>& C, Lane<S>& L, int t, uns
     if (t < 4) return;  // rings not primed yet
   }
   // ---- stage B: step_height of column js = ce - 2 (ages: js+1 -> 1, js -> 2, js-1 -> 3) ---------
-  const unsigned shcol = C.sh_lane + (t & 1) * SHBUF_BYTES;
+  const unsigned shcol = C.sh_lane + (PH % NSHB) * SHBUF_BYTES;
+  // column tips of this step: one broadcast word from the stage's padding, a byte per tip (0x00 = inside the window,
+  // 0xff = excluded); replicated into all four bytes it is +0.0 or a NaN to add to the tip value (see fill_colmask)
+  unsigned cmw = 0u;
+  if constexpr (S::MASKS) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(cmw) : "r"(C.e_base + stage * STAGE_BYTES + (STAGE_PAD + PH * 4)));
   f2 V0;
   {
     float mn2[2], mx2[2];
@@ -585,9 +631,8 @@ __device__ __forceinline__ void march_step(StepCtx<S>& C, Lane<S>& L, int t, uns
     }
     f2 TL1 = L.e[S4], TR1 = L.e[S0];
     if constexpr (S::TIP1) {
-      const float qn = __int_as_float(0x7fc00000);
-      TL1 = add2(TL1, bc((cm_js & 1u) ? 0.0f : qn));
-      TR1 = add2(TR1, bc((cm_js & 2u) ? 0.0f : qn));
+      TL1 = add2(TL1, bc(__uint_as_float(__byte_perm(cmw, 0u, 0x0000))));
+      TR1 = add2(TR1, bc(__uint_as_float(__byte_perm(cmw, 0u, 0x1111))));
     }
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
@@ -643,7 +688,7 @@ __device__ __forceinline__ void march_step(StepCtx<S>& C, Lane<S>& L, int t, uns
     if constexpr (S::W20 == 2) {
       PC = add2(PC, add2(mk(f[0], f[1]), mk(f[4], f[5])));
     } else if constexpr (S::TIP2) {  // NaN > crit is false
-      PC = add2(PC, add2(mk(gtf(lo(SU), A.step_cmp), gtf(hi(SU), A.step_cmp)), mk(gtf(lo(SD), A.step_cmp), gtf(hi(SD), A.step_cmp))));
+      PC = fma2(mk(f[0], f[1]), C.cntU2, fma2(mk(f[4], f[5]), C.cntD2, PC));  // the tips' flags exist already: weight them (0/1, exact)
     }
     L.sh[S0] = V0;
     ring_put<R_S3MX, S0>(C, L.s3mx, mk(smx[0], smx[1])); ring_put<R_S3C, S0>(C, L.s3c, mk(sc[0], sc[1]));
@@ -693,12 +738,10 @@ __device__ __forceinline__ void march_step(StepCtx<S>& C, Lane<S>& L, int t, uns
   const bool st_ok = C.out_ok && (unsigned)(t - 8) < (unsigned)C.len;  // column jo = ce - 4 = q0 + t - 8 belongs to the unit
   {
     float mx2[2];
-    unsigned sflag = 0;
     f2 TL2 = L.sh[S4], TR2 = L.sh[S0];
     if constexpr (S::TIP2) {
-      const float qn = __int_as_float(0x7fc00000);
-      TL2 = add2(TL2, bc((cm_jo & 4u) ? 0.0f : qn));
-      TR2 = add2(TR2, bc((cm_jo & 8u) ? 0.0f : qn));
+      TL2 = add2(TL2, bc(__uint_as_float(__byte_perm(cmw, 0u, 0x2222))));
+      TR2 = add2(TR2, bc(__uint_as_float(__byte_perm(cmw, 0u, 0x3333))));
     }
     f2 s3mxA = 0ull, s3mxB = 0ull;
     if constexpr (S::W21 >= 0) { s3mxA = ring_get<R_S3MX, S1, S0>(C, L.s3mx); s3mxB = ring_get<R_S3MX, S3, S0>(C, L.s3mx); }
@@ -712,7 +755,6 @@ __device__ __forceinline__ void march_step(StepCtx<S>& C, Lane<S>& L, int t, uns
       float mx = R(L.pcmx[S2]);
       if constexpr (S::W21 >= 0) mx = max3n(mx, R(s3mxA), R(s3mxB));
       if constexpr (S::W22 == 0 || S::TIP2) mx = max3n(mx, R(TL2), R(TR2));
-      sflag |= (mx > 3.0e38f) ? (1u << r) : 0u;  // an infinite elevation reached the window: the slow path sorts it out
       mx2[r] = mx;
     }
     const f2 MX = mk(mx2[0], mx2[1]);
@@ -730,9 +772,13 @@ __device__ __forceinline__ void march_step(StepCtx<S>& C, Lane<S>& L, int t, uns
       *reinterpret_cast<f2*>(A.step + oc) = outv;
       *reinterpret_cast<f2*>(A.trav + oc) = tr;
     }
-    // certified slow path: append flagged cells (bit 30: normals part, bit 31: step part)
-    const unsigned fl = st_ok ? (nf | (sflag << 2)) : 0u;  // bits 0/1: normals part of row x/y, bits 2/3: step part
-    if (__any_sync(FULL, fl != 0u)) append_flagged(A.count, A.list, A.cap, C.lstate, C.lane, oc, fl);
+    // certified slow path: append flagged cells (bit 30: normals part, bit 31: step part).  An infinite elevation that reached
+    // the step window (maxNum skips NaN: the larger row maximum is +Inf iff one of them is) is sorted out there as well.
+    const bool any_inf = fmaxf(mx2[0], mx2[1]) > 3.0e38f;
+    if (__any_sync(FULL, st_ok && (nf != 0u || any_inf))) {
+      const unsigned sflag = (mx2[0] > 3.0e38f ? 1u : 0u) | (mx2[1] > 3.0e38f ? 2u : 0u);
+      append_flagged(A.count, A.list, A.cap, C.lstate, C.lane, oc, st_ok ? (nf | (sflag << 2)) : 0u);  // bits 0/1: normals part of row x/y, bits 2/3: step part
+    }
   }
 }
 
@@ -744,7 +790,7 @@ __global__ void TE_KERNEL_ATTR k_chain_fused(const __grid_constant__ CUtensorMap
   const unsigned wbase = smem_u32(smem_raw) + warp * WARP_SMEM_BYTES;
   const unsigned ering = wbase;
   const unsigned shbuf = wbase + NST * STAGE_BYTES;
-  const unsigned bar0 = shbuf + 2 * SHBUF_BYTES;
+  const unsigned bar0 = wbase + WARP_AUX_OFF;
   if (lane == 0) {
     for (int s = 0; s < NST; ++s) mbar_init(bar0 + 8 * s, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -757,8 +803,8 @@ __global__ void TE_KERNEL_ATTR k_chain_fused(const __grid_constant__ CUtensorMap
   unsigned kglob = 0;  // chunks consumed so far by this warp (stage = kglob % NST, parity = (kglob / NST) & 1)
 
   Lane<S> L{};  // the warm-up steps of a unit read ring slots before they are written (results discarded)
-  StepCtx<S> C{A, ering + lane * 8u, shbuf + lane * 8u, lane, 0, 0, 0, 0ull, 0ull, 0ull, 0ull,
-               reinterpret_cast<f2*>(smem_raw + warp * WARP_SMEM_BYTES + (NST * STAGE_BYTES + 2 * SHBUF_BYTES + 64)) + lane,
+  StepCtx<S> C{A, ering, ering + lane * 8u, shbuf + lane * 8u, lane, 0, 0, 0, 0ull, 0ull, 0ull, 0ull, 0ull, 0ull,
+               reinterpret_cast<f2*>(smem_raw + warp * WARP_SMEM_BYTES + WARP_RING_OFF) + lane,
                bar0 + 8 * NST, false, 0u, 0};
   if (lane == 0) asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(C.lstate), "r"(0u), "r"(LIST_CHUNK) : "memory");  // no chunk yet
   __syncwarp();
@@ -791,6 +837,8 @@ __global__ void TE_KERNEL_ATTR k_chain_fused(const __grid_constant__ CUtensorMap
       C.tipD1 = mk((rm0 & 2u) ? 0.f : qn, (rm1 & 2u) ? 0.f : qn);
       C.tipU2 = mk((rm0 & 4u) ? 0.f : qn, (rm1 & 4u) ? 0.f : qn);
       C.tipD2 = mk((rm0 & 8u) ? 0.f : qn, (rm1 & 8u) ? 0.f : qn);
+      C.cntU2 = mk((rm0 & 4u) ? 1.f : 0.f, (rm1 & 4u) ? 1.f : 0.f);
+      C.cntD2 = mk((rm0 & 8u) ? 1.f : 0.f, (rm1 & 8u) ? 1.f : 0.f);
     }
     __syncwarp();  // every lane is done with the previous unit's smem
     const unsigned kbase = kglob;
@@ -801,12 +849,8 @@ __global__ void TE_KERNEL_ATTR k_chain_fused(const __grid_constant__ CUtensorMap
         tma_load_3d(ering + st * STAGE_BYTES, &map, C.s0 - 2, (C.q0 - 4 + CH * k) - A.in_col0, mapi, bar0 + 8 * st);
       }
     }
-    // column masks of the first chunk (lane l holds column cbase + l - 8)
-    unsigned cm_cur = 0, cm_next = 0;
-    if constexpr (S::MASKS) {
-      const int c = C.q0 - 4 + lane - 8;
-      cm_cur = (lane < 16 && c >= 0 && c < A.cols_total) ? A.colmask[c] : 0u;
-    }
+    // column masks of the first chunk
+    if constexpr (S::MASKS) fill_colmask(A, ering + (kbase % NST) * STAGE_BYTES, C.q0 - 4, lane);
     for (int kc = 0; kc < nchunks; ++kc) {
       const unsigned st = (kbase + kc) % NST;
       __syncwarp();  // all lanes finished the previous chunk: its predecessor's stage may be refilled
@@ -815,28 +859,14 @@ __global__ void TE_KERNEL_ATTR k_chain_fused(const __grid_constant__ CUtensorMap
         mbar_expect_tx(bar0 + 8 * sn, EROWS * CH * 4);
         tma_load_3d(ering + sn * STAGE_BYTES, &map, C.s0 - 2, (C.q0 - 4 + CH * (kc + NST - 2)) - A.in_col0, mapi, bar0 + 8 * sn);
       }
-      if constexpr (S::MASKS) {
-        const int c = C.q0 - 4 + CH * (kc + 1) + lane - 8;
-        cm_next = (lane < 16 && c >= 0 && c < A.cols_total) ? A.colmask[c] : 0u;
-      }
+      if constexpr (S::MASKS) fill_colmask(A, ering + ((kbase + kc + 1) % NST) * STAGE_BYTES, C.q0 - 4 + CH * (kc + 1), lane);  // next chunk's
       mbar_wait(bar0 + 8 * st, ((kbase + kc) / NST) & 1u);
       const int t0 = kc * CH;
-      unsigned mjs[CH], mjo[CH];
-#pragma unroll
-      for (int ph = 0; ph < CH; ++ph) {
-        if constexpr (S::MASKS) {
-          mjs[ph] = __shfl_sync(FULL, cm_cur, ph + 6);  // js = ce - 2
-          mjo[ph] = __shfl_sync(FULL, cm_cur, ph + 4);  // jo = ce - 4
-        } else {
-          mjs[ph] = mjo[ph] = 0u;
-        }
-      }
-      march_step<S, 0, KN>(C, L, t0 + 0, st, mjs[0], mjo[0]);
-      march_step<S, 1, KN>(C, L, t0 + 1, st, mjs[1], mjo[1]);
-      march_step<S, 2, KN>(C, L, t0 + 2, st, mjs[2], mjo[2]);
-      march_step<S, 3, KN>(C, L, t0 + 3, st, mjs[3], mjo[3]);
-      march_step<S, 4, KN>(C, L, t0 + 4, st, mjs[4], mjo[4]);
-      cm_cur = cm_next;
+      march_step<S, 0, KN>(C, L, t0 + 0, st);
+      march_step<S, 1, KN>(C, L, t0 + 1, st);
+      march_step<S, 2, KN>(C, L, t0 + 2, st);
+      march_step<S, 3, KN>(C, L, t0 + 3, st);
+      march_step<S, 4, KN>(C, L, t0 + 4, st);
     }
     kglob += nchunks;
     unit = __shfl_sync(FULL, next, 0);
