@@ -197,11 +197,20 @@ int te_footprint2(te_ctx* ctx, const te_geometry* g, const te_slab* slab, const 
  * path of one pose the circle at the pose is checked (:365-390), otherwise every fourth cell (nSkip = 3, :401) of the grid line
  * between consecutive poses, and the segment means are combined weighted by segment length (:437-449).  Outputs per path:
  * TraversabilityResult.is_safe and .traversability (0 when unsafe); .area is 0 for circular footprints.  Not covered:
- * checkRobotInclination_ (:359, :386), the untraversable polygon, publishing.  Poses of a multi-pose path must lie inside the map
+ * the untraversable polygon, publishing.  Poses of a multi-pose path must lie inside the map
  * (the reference does not check getIndex's return value there): such a path is reported unsafe. */
 int te_check_footprint_paths(te_ctx* ctx, const te_geometry* g, const float* traversability_footprint,
                              double traversability_default, int32_t npaths, const int32_t* path_begin, const double* poses_xy,
                              uint8_t* is_safe, double* traversability, int memory);
+
+/* te_check_footprint_paths with checkRobotInclination_ set (TraversabilityMap.cpp:359-363, :386-390): before the circles of a
+ * pose / segment are looked at, TraversabilityMap::checkInclination (:748-762) reads the `robot_slope` layer (robotSlopeType_,
+ * config/robot.yaml:1; column-major like every layer) — at the pose for a single pose, along LineIterator(start, end) otherwise,
+ * skipping invalid cells — and the path is unsafe as soon as a cell is exactly 0.0.  robot_slope_or_null == NULL is the call above.
+ * A single pose outside the map (the reference's atPosition throws) is reported unsafe. */
+int te_check_footprint_paths2(te_ctx* ctx, const te_geometry* g, const float* traversability_footprint,
+                              const float* robot_slope_or_null, double traversability_default, int32_t npaths,
+                              const int32_t* path_begin, const double* poses_xy, uint8_t* is_safe, double* traversability, int memory);
 
 /* ---- Multi-GPU: one map tiled into column slabs, one process (rank) per GPU -------------------------------
  * The chain and the footprint sweep are stencils of fixed radius, so the only exchange step is a one-shot copy of the

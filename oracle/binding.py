@@ -160,18 +160,20 @@ def footprint(g, fp, traversability, slope_l, step_l, elevation, nthreads=0, rou
     return out, sfp, stfp, rfp
 
 
-def check_circular_paths(g, footprint_layer, traversability_default, path_begin, poses_xy):
-    """(is_safe uint8[npaths], traversability float64[npaths]) of TraversabilityMap::checkCircularFootprintPath per path."""
+def check_circular_paths(g, footprint_layer, traversability_default, path_begin, poses_xy, robot_slope=None):
+    """(is_safe uint8[npaths], traversability float64[npaths]) of TraversabilityMap::checkCircularFootprintPath per path;
+    robot_slope: the layer checkInclination reads when checkRobotInclination_ is set (None: off)."""
     f = _layer(g, footprint_layer)
+    rs = _layer(g, robot_slope) if robot_slope is not None else None
     pb = np.ascontiguousarray(path_begin, dtype=np.int32)
     xy = np.ascontiguousarray(poses_xy, dtype=np.float64)
     n = len(pb) - 1
     safe = np.zeros(n, dtype=np.uint8)
     trav = np.zeros(n, dtype=np.float64)
     L = lib()
-    L.teo_check_circular_paths.argtypes = [C.POINTER(Geometry), C.c_void_p, C.c_double, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
-    rc = L.teo_check_circular_paths(C.byref(g), f.ctypes.data, traversability_default, n, pb.ctypes.data, xy.ctypes.data,
-                                    safe.ctypes.data, trav.ctypes.data)
+    L.teo_check_circular_paths2.argtypes = [C.POINTER(Geometry), C.c_void_p, C.c_void_p, C.c_double, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    rc = L.teo_check_circular_paths2(C.byref(g), f.ctypes.data, rs.ctypes.data if rs is not None else None, traversability_default, n,
+                                     pb.ctypes.data, xy.ctypes.data, safe.ctypes.data, trav.ctypes.data)
     assert rc == 0, rc
     return safe, trav
 

@@ -100,6 +100,10 @@ int teo_footprint2(const teo_geometry* g, const teo_footprint_params* p, const f
 int teo_check_circular_paths(const teo_geometry* g, const float* traversability_footprint, double traversability_default,
                              int npaths, const int32_t* path_begin, const double* poses_xy, uint8_t* is_safe,
                              double* traversability);
+/* ... with checkRobotInclination_ (checkInclination, TraversabilityMap.cpp:748-762) on the `robot_slope` layer (NULL: off). */
+int teo_check_circular_paths2(const teo_geometry* g, const float* traversability_footprint, const float* robot_slope_or_null,
+                              double traversability_default, int npaths, const int32_t* path_begin, const double* poses_xy,
+                              uint8_t* is_safe, double* traversability);
 
 /* Visit order of grid_map::SpiralIterator for a centre far from the map border: writes up to `cap`
  * (di,dj) pairs, returns the number of cells visited.  radius/resolution in metres. */

@@ -243,6 +243,34 @@ SpiralOffsets spiral_offsets(double radius, double res) {
   return s;
 }
 
+// isTraversableForFilters (TraversabilityMap.cpp:774-792) is a pure function of the layers: evaluated once per cell.
+void compute_blocked(const Map& m, const teo_footprint_params& prm, const float* rough, std::vector<unsigned char>& blocked,
+                     float* slope_fp, float* step_fp, float* rough_fp, int nt) {
+  const teo_footprint_params* p = &prm;
+  const size_t n = (size_t)m.rows * m.cols;
+  blocked.assign(n, 0);
+#pragma omp parallel for schedule(dynamic, 8) num_threads(nt)
+  for (int j = 0; j < m.cols; ++j)
+    for (int i = 0; i < m.rows; ++i) {
+      const size_t c = (size_t)j * m.rows + i;
+      const bool s_ok = check_slope(m, *p, i, j);
+      bool t_ok = true;
+      if (slope_fp) slope_fp[c] = (m.at(m.slope, i, j) == 0.0) ? (s_ok ? 1.0f : 0.0f) : kNaNf;  // :887,:883
+      if (step_fp) step_fp[c] = kNaNf;
+      if (s_ok) {                                                                      // short-circuit of :777-778
+        t_ok = check_step(m, *p, i, j);
+        if (step_fp && m.at(m.step, i, j) == 0.0) step_fp[c] = t_ok ? 1.0f : 0.0f;     // :859,:842,:854
+      }
+      bool r_ok = true;
+      if (rough_fp) rough_fp[c] = kNaNf;
+      if (s_ok && t_ok && p->verify_roughness) {                                       // :779-783: only after slope and step passed
+        r_ok = check_roughness(m, *p, rough, i, j);
+        if (rough_fp && (double)rough[c] == 0.0) rough_fp[c] = r_ok ? 1.0f : 0.0f;     // :915,:911
+      }
+      blocked[c] = !(s_ok && t_ok && r_ok);
+    }
+}
+
 }  // namespace
 
 extern "C" {
@@ -285,29 +313,8 @@ int teo_footprint2(const teo_geometry* g, const teo_footprint_params* p, const f
   (void)nthreads;
 #endif
   (void)nt;
-  const size_t n = (size_t)m.rows * m.cols;
-  // isTraversableForFilters (:774-792) is a pure function of the layers: evaluate it once per cell.
-  std::vector<unsigned char> blocked(n);
-#pragma omp parallel for schedule(dynamic, 8) num_threads(nt)
-  for (int j = 0; j < m.cols; ++j)
-    for (int i = 0; i < m.rows; ++i) {
-      const size_t c = (size_t)j * m.rows + i;
-      const bool s_ok = check_slope(m, *p, i, j);
-      bool t_ok = true;
-      if (slope_fp) slope_fp[c] = (m.at(m.slope, i, j) == 0.0) ? (s_ok ? 1.0f : 0.0f) : kNaNf;  // :887,:883
-      if (step_fp) step_fp[c] = kNaNf;
-      if (s_ok) {                                                                      // short-circuit of :777-778
-        t_ok = check_step(m, *p, i, j);
-        if (step_fp && m.at(m.step, i, j) == 0.0) step_fp[c] = t_ok ? 1.0f : 0.0f;     // :859,:842,:854
-      }
-      bool r_ok = true;
-      if (rough_fp) rough_fp[c] = kNaNf;
-      if (s_ok && t_ok && p->verify_roughness) {                                       // :779-783: only after slope and step passed
-        r_ok = check_roughness(m, *p, rough, i, j);
-        if (rough_fp && (double)rough[c] == 0.0) rough_fp[c] = r_ok ? 1.0f : 0.0f;     // :915,:911
-      }
-      blocked[c] = !(s_ok && t_ok && r_ok);
-    }
+  std::vector<unsigned char> blocked;
+  compute_blocked(m, *p, rough, blocked, slope_fp, step_fp, rough_fp, nt);
 
   const double radiusMin = p->radius;                         // :313  isTraversable(center, radius + offset, traversability, radius)
   const double radiusMax = p->radius + p->offset;
@@ -368,6 +375,15 @@ int teo_footprint2(const teo_geometry* g, const teo_footprint_params* p, const f
 // length is used here.
 int teo_check_circular_paths(const teo_geometry* g, const float* footprint, double traversability_default, int npaths,
                              const int32_t* path_begin, const double* poses_xy, uint8_t* is_safe, double* traversability) {
+  return teo_check_circular_paths2(g, footprint, nullptr, traversability_default, npaths, path_begin, poses_xy, is_safe, traversability);
+}
+
+// The same with checkRobotInclination_ set (TraversabilityMap.cpp:359-363, :386-390): `robot_slope` is the layer robotSlopeType_
+// names (robot.yaml:1), NULL switches the check off.  checkInclination, TraversabilityMap.cpp:748-762: a single pose reads the
+// layer at the pose (a pose outside the map makes atPosition throw: reported unsafe here); two poses walk
+// LineIterator(startIndex, endIndex), skip invalid cells (:757) and fail on a cell that is exactly 0.0 (:758).
+int teo_check_circular_paths2(const teo_geometry* g, const float* footprint, const float* robot_slope, double traversability_default,
+                              int npaths, const int32_t* path_begin, const double* poses_xy, uint8_t* is_safe, double* traversability) {
   if (!g || g->rows <= 0 || g->cols <= 0 || !footprint || npaths < 0 || !path_begin || !poses_xy || !is_safe || !traversability) return 1;
   Map m{g->rows, g->cols, g->resolution, {g->length_x, g->length_y}, {g->position_x, g->position_y}, nullptr, nullptr, nullptr, nullptr, {}, {}};
   m.X.resize(m.rows);
@@ -383,6 +399,24 @@ int teo_check_circular_paths(const teo_geometry* g, const float* footprint, doub
     t = (double)footprint[(size_t)j * m.rows + i];                          // :668
     return t != 0.0;                                                         // :669
   };
+  auto inclination_ok = [&](V2 start, V2 end) -> bool {                       // checkInclination, :748-762
+    if (!robot_slope) return true;                                           // checkRobotInclination_ off
+    if (end.x == start.x && end.y == start.y) {                              // :750
+      int i, j;
+      if (!is_inside(m, start) || !get_index(m, start, i, j)) return false;  // atPosition would throw
+      return !(robot_slope[(size_t)j * m.rows + i] == 0.0f);                 // :751
+    }
+    int si, sj, ei, ej;
+    if (!get_index(m, start, si, sj) || !get_index(m, end, ei, ej)) return false;  // poses must lie in the map
+    bool ok = true;
+    for_line(si, sj, ei, ej, [&](int a, int c2) {                            // :756 LineIterator(startIndex, endIndex)
+      const float v = robot_slope[(size_t)c2 * m.rows + a];
+      if (!std::isfinite(v)) return true;                                    // :757
+      if (v == 0.0f) { ok = false; return false; }                           // :758
+      return true;
+    });
+    return ok;
+  };
   for (int q = 0; q < npaths; ++q) {
     const int b = path_begin[q], n = path_begin[q + 1] - b;
     is_safe[q] = 0;                                                          // :352-353
@@ -395,11 +429,13 @@ int teo_check_circular_paths(const teo_geometry* g, const float* footprint, doub
       start = end;                                                           // :361
       end = V2{poses_xy[2 * (b + k)], poses_xy[2 * (b + k) + 1]};            // :362-363
       if (n == 1) {                                                          // :365
+        if (!inclination_ok(end, end)) { ok = false; break; }                // :366-370
         double t;
         if (!circle(end, t)) { ok = false; break; }                          // :371-388
         result = t;                                                          // :389
       }
       if (n > 1 && k > 0) {                                                  // :392
+        if (!inclination_ok(start, end)) { ok = false; break; }              // :393-397
         int si, sj, ei, ej;
         if (!get_index(m, start, si, sj) || !get_index(m, end, ei, ej)) { ok = false; break; }  // poses must lie in the map
         double sum = 0.0;

@@ -187,3 +187,12 @@ def test_batched_circular_footprint_paths(te, ctx, oracle):
     assert np.array_equal(safe, ref_safe)
     assert np.array_equal(t, ref_t)                                     # same double arithmetic, bit for bit
     assert 10 < int(safe.sum()) < 390 and safe[0] == 0                   # safe and unsafe paths both occur; the empty path is unsafe
+    # checkRobotInclination_ (TraversabilityMap.cpp:359-363, 386-390 -> checkInclination :748-762) on a robot_slope layer with
+    # zero patches and holes: fewer safe paths, same arithmetic for the survivors
+    rs = np.asfortranarray(ch["slope"].copy())
+    rs[rng.random(rs.shape) < 0.002] = 0.0
+    rs[rng.random(rs.shape) < 0.05] = np.nan
+    ref_safe2, ref_t2 = oracle.check_circular_paths(og, fpl, fo.traversability_default, begin, poses, robot_slope=rs)
+    safe2, t2 = ctx.check_footprint_paths(g, fpl, fo.traversability_default, begin, poses, robot_slope=rs)
+    assert np.array_equal(safe2, ref_safe2) and np.array_equal(t2, ref_t2)
+    assert int(safe2.sum()) < int(safe.sum()) and not (safe2 & ~safe).any()

@@ -75,3 +75,25 @@ def test_check_for_roughness_blocks_rough_patches(oracle):
     assert out[20, 20] == 0.0 and rfp[20, 20] == 0.0          # deep inside the patch: 29 zero cells > 22
     assert out[10, 10] == 1.0 and rfp[10, 10] == 1.0          # the patch corner sees only ~11 zero cells
     assert out[5, 5] == 1.0 and np.isnan(rfp[5, 5])           # not a zero-roughness cell: the check is skipped (:897)
+
+
+def test_check_inclination_in_path_check(oracle):
+    """checkInclination (TraversabilityMap.cpp:748-762) inside checkCircularFootprintPath (:359-363, :386-390): a zero of the
+    robot_slope layer at a single pose, or on the grid line between two poses, makes the path unsafe; invalid cells are skipped."""
+    rows, cols = 64, 64
+    g = oracle.Geometry.make(rows, cols, 0.02)
+    fp = np.asfortranarray(np.full((rows, cols), 0.8, dtype=np.float32))
+    rs = np.asfortranarray(np.ones((rows, cols), dtype=np.float32))
+    x = lambda i: 0.5 * rows * 0.02 - 0.01 - 0.02 * i   # cell centre of row index i (map centred at 0)
+    y = lambda j: 0.5 * cols * 0.02 - 0.01 - 0.02 * j
+    poses = np.array([[x(10), y(10)], [x(20), y(20)], [x(20), y(40)], [x(30), y(5)]])
+    begin = [0, 1, 3, 4]                                # single pose, one segment along row 20, single pose
+    safe, t = oracle.check_circular_paths(g, fp, 0.3, begin, poses, robot_slope=rs)
+    assert safe.tolist() == [1, 1, 1] and np.allclose(t, 0.8)
+    rs2 = rs.copy(); rs2[10, 10] = 0.0                  # at the first pose
+    assert oracle.check_circular_paths(g, fp, 0.3, begin, poses, robot_slope=rs2)[0].tolist() == [0, 1, 1]
+    rs3 = rs.copy(); rs3[20, 30] = 0.0                  # on the line of the segment
+    assert oracle.check_circular_paths(g, fp, 0.3, begin, poses, robot_slope=rs3)[0].tolist() == [1, 0, 1]
+    rs4 = rs.copy(); rs4[20, 30] = np.nan; rs4[21, 30] = 0.0   # an invalid cell on the line is skipped, a zero next to the line is not seen
+    assert oracle.check_circular_paths(g, fp, 0.3, begin, poses, robot_slope=rs4)[0].tolist() == [1, 1, 1]
+    assert oracle.check_circular_paths(g, fp, 0.3, begin, poses)[0].tolist() == [1, 1, 1]   # check off

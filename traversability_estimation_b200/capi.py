@@ -18,7 +18,7 @@ KERNEL_AUTO, KERNEL_GENERIC, KERNEL_FUSED = 0, 1, 2
 
 EXPORTS = ["te_create", "te_destroy", "te_last_error", "te_abi_version", "te_set_stream", "te_synchronize",
            "te_set_kernel", "te_get_stats", "te_enable_timing", "te_get_timing", "te_get_flag_counters", "te_get_escalation_stats", "te_fused_plan", "te_slope", "te_normals", "te_step", "te_roughness", "te_chain",
-           "te_chain_batched", "te_footprint", "te_footprint2", "te_check_footprint_paths", "te_ipc_export", "te_ipc_open", "te_ipc_close", "te_event_create_ipc", "te_event_open_ipc",
+           "te_chain_batched", "te_footprint", "te_footprint2", "te_check_footprint_paths", "te_check_footprint_paths2", "te_ipc_export", "te_ipc_open", "te_ipc_close", "te_event_create_ipc", "te_event_open_ipc",
            "te_event_record", "te_event_destroy", "te_halo_pull", "te_host_alloc", "te_host_free"]
 
 
@@ -270,17 +270,20 @@ class Context:
                                               _addr(traversability), _addr(slope), _addr(step), _addr(roughness), _addr(elevation),
                                               _addr(out), _addr(slope_fp), _addr(step_fp), _addr(roughness_fp), memory))
 
-    def check_footprint_paths(self, g, footprint_layer, traversability_default, path_begin, poses_xy):
-        """Host convenience: (is_safe uint8[npaths], traversability float64[npaths]); footprint_layer is a column-major host layer."""
+    def check_footprint_paths(self, g, footprint_layer, traversability_default, path_begin, poses_xy, robot_slope=None):
+        """Host convenience: (is_safe uint8[npaths], traversability float64[npaths]); footprint_layer is a column-major host layer;
+        robot_slope (optional layer) switches checkRobotInclination_ on."""
         f = np.asfortranarray(footprint_layer, dtype=np.float32)
+        rs = np.asfortranarray(robot_slope, dtype=np.float32) if robot_slope is not None else None
         pb = np.ascontiguousarray(path_begin, dtype=np.int32)
         xy = np.ascontiguousarray(poses_xy, dtype=np.float64)
         n = len(pb) - 1
         safe, trav = np.zeros(n, dtype=np.uint8), np.zeros(n, dtype=np.float64)
-        self._L.te_check_footprint_paths.argtypes = [C.c_void_p, C.POINTER(Geometry), C.c_void_p, C.c_double, C.c_int32, C.c_void_p,
-                                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
-        self._check(self._L.te_check_footprint_paths(self._h, C.byref(g), f.ctypes.data, traversability_default, n, pb.ctypes.data,
-                                                     xy.ctypes.data, safe.ctypes.data, trav.ctypes.data, MEM_HOST))
+        self._L.te_check_footprint_paths2.argtypes = [C.c_void_p, C.POINTER(Geometry), C.c_void_p, C.c_void_p, C.c_double, C.c_int32, C.c_void_p,
+                                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        self._check(self._L.te_check_footprint_paths2(self._h, C.byref(g), f.ctypes.data, rs.ctypes.data if rs is not None else None,
+                                                      traversability_default, n, pb.ctypes.data, xy.ctypes.data, safe.ctypes.data,
+                                                      trav.ctypes.data, MEM_HOST))
         return safe, trav
 
     # ---- multi-GPU halo (te_halo_pull and the IPC helpers around it)

@@ -93,6 +93,10 @@ struct te_ctx {
 
   DevBuf stage[12];          // TE_MEM_HOST staging: 0..3 inputs, 4..11 outputs
   DevBuf worklist, worklist3, counter;  // fused-kernel fix-up lists (tier 2, tier 3) and their counters
+  // The counters are two 512-byte blocks used alternately: the last kernel of a chain call (k_fixup_cells) zeroes the block of the
+  // NEXT call, so a call needs no cudaMemsetAsync of its own (one stream operation and one launch gap less per map).
+  int counter_phase = 0;    // block of the most recent fused launch (what the statistics entry points read)
+  int counter_clean = -1;   // block known to be zero on the stream (-1: none)
   te::FusedState fused;      // tensor maps / tables of the fused stencil
   te::FootprintState fp;
 
@@ -273,28 +277,38 @@ int run_chain_device(te_ctx* c, const te_geometry* g, const te::SlabView& v, con
     if (cap >= ((size_t)1 << 32)) return fail(TE_ERR_UNSUPPORTED, "launch of %zu cells exceeds the work-list index range", cells);
     TE_CUDA(c->worklist.reserve(sizeof(unsigned) * cap));
     TE_CUDA(c->worklist3.reserve(sizeof(unsigned) * cells));
-    TE_CUDA(c->counter.reserve(sizeof(unsigned) * 128));
+    {
+      const void* before = c->counter.p;
+      TE_CUDA(c->counter.reserve(sizeof(unsigned) * 256));
+      if (c->counter.p != before) c->counter_clean = -1;
+    }
     {  // one launch covers every map of the batch
       const te::ChainOut& om = o;
-      TE_CUDA(cudaMemsetAsync(c->counter.p, 0, sizeof(unsigned) * 128, c->stream));
+      const int phase = c->counter_phase ^ 1;
+      unsigned* const cnt = (unsigned*)c->counter.p + 128 * phase;
+      unsigned* const cnt_next = (unsigned*)c->counter.p + 128 * (phase ^ 1);
+      if (c->counter_clean != phase) TE_CUDA(cudaMemsetAsync(cnt, 0, sizeof(unsigned) * 128, c->stream));
+      c->counter_clean = -1;
+      c->counter_phase = phase;
       te_ctx::Ev3* ev = nullptr;
       if (c->timing) {
         if (int rc = next_timing_slot(c, &ev)) return rc;
         TE_CUDA(cudaEventRecord(ev->a, c->stream));
       }
-      int rc = te::launch_chain_fused(c->fused, v, d, nmaps, elev, om, (unsigned*)c->worklist.p, (unsigned*)c->counter.p,
-                                      (unsigned)cap, c->sms, c->stream);
+      int rc = te::launch_chain_fused(c->fused, v, d, nmaps, elev, om, (unsigned*)c->worklist.p, cnt, (unsigned)cap, c->sms, c->stream);
       if (rc != 0) return fail(TE_ERR_CUDA, "fused chain launch failed: %s", c->fused.why.c_str());
       if (int r2 = launch_check(c, "k_chain_fused")) return r2;
       if (c->timing) TE_CUDA(cudaEventRecord(ev->b, c->stream));
       te::FixupArgs fa;
       te::make_fixup_args(c->fused, v, d, &fa);
-      te::launch_fixup_t2(fa, elev, om, (const unsigned*)c->worklist.p, (const unsigned*)c->counter.p, (unsigned)cap,
-                          (unsigned*)c->worklist3.p, (unsigned*)c->counter.p + 4, (unsigned)cells, c->sms, c->stream);
+      // tiers 2 and 3 are programmatic dependent launches unless events are recorded in between (timing): their grids are set
+      // up while the predecessor drains and wait on griddepcontrol.wait before they read the lists
+      te::launch_fixup_t2(fa, elev, om, (const unsigned*)c->worklist.p, cnt, (unsigned)cap, (unsigned*)c->worklist3.p, cnt + 4,
+                          (unsigned)cells, c->sms, c->stream, !c->timing);
       if (int r2 = launch_check(c, "k_fixup_t2")) return r2;
-      te::launch_fixup(v, d, elev, om, (const unsigned*)c->worklist3.p, (const unsigned*)c->counter.p + 4, (unsigned)cells, c->sms,
-                       c->stream);
+      te::launch_fixup(v, d, elev, om, (const unsigned*)c->worklist3.p, cnt + 4, (unsigned)cells, cnt_next, c->sms, c->stream, true);
       if (int r2 = launch_check(c, "k_fixup_cells")) return r2;
+      c->counter_clean = phase ^ 1;  // k_fixup_cells zeroes the other block
       if (c->timing) {
         TE_CUDA(cudaEventRecord(ev->c, c->stream));
         ++c->events_used;
@@ -423,7 +437,7 @@ int te_get_stats(te_ctx* c, int64_t* launches, int64_t* slow) {
     unsigned last[4] = {0, 0, 0, 0};
     if (c->counter.p) {
       TE_CUDA(cudaStreamSynchronize(c->stream));
-      TE_CUDA(cudaMemcpy(last, c->counter.p, sizeof(last), cudaMemcpyDeviceToHost));
+      TE_CUDA(cudaMemcpy(last, (unsigned*)c->counter.p + 128 * c->counter_phase, sizeof(last), cudaMemcpyDeviceToHost));
     }
     *slow = (int64_t)last[1];  // cells flagged (word 0 counts reserved list entries, chunk padding included)
   }
@@ -470,7 +484,7 @@ int te_get_flag_counters(te_ctx* c, uint32_t out[5]) {
   if (c->counter.p) {
     unsigned raw[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     TE_CUDA(cudaStreamSynchronize(c->stream));
-    TE_CUDA(cudaMemcpy(raw, c->counter.p, sizeof(raw), cudaMemcpyDeviceToHost));
+    TE_CUDA(cudaMemcpy(raw, (unsigned*)c->counter.p + 128 * c->counter_phase, sizeof(raw), cudaMemcpyDeviceToHost));
     out[0] = raw[1];            // cells flagged by the fp32 stencil
     out[1] = raw[0];            // list entries reserved (warp-private chunks, padding included)
     out[2] = raw[2] | raw[5];   // a work list overflowed (never: the lists hold every cell of the launch)
@@ -486,7 +500,7 @@ int te_get_escalation_stats(te_ctx* c, uint32_t reasons[16], uint32_t valid_cell
   std::memset(raw, 0, sizeof(raw));
   if (c->counter.p) {
     TE_CUDA(cudaStreamSynchronize(c->stream));
-    TE_CUDA(cudaMemcpy(raw, c->counter.p, sizeof(raw), cudaMemcpyDeviceToHost));
+    TE_CUDA(cudaMemcpy(raw, (unsigned*)c->counter.p + 128 * c->counter_phase, sizeof(raw), cudaMemcpyDeviceToHost));
   }
   for (int k = 0; k < 16; ++k) reasons[k] = raw[8 + k];
   for (int k = 0; k < 26; ++k) valid_cells[k] = raw[24 + k];
@@ -804,6 +818,12 @@ int te_footprint(te_ctx* c, const te_geometry* g, const te_slab* slab, const te_
 
 int te_check_footprint_paths(te_ctx* c, const te_geometry* g, const float* footprint, double traversability_default, int32_t npaths,
                              const int32_t* path_begin, const double* poses_xy, uint8_t* is_safe, double* traversability, int memory) {
+  return te_check_footprint_paths2(c, g, footprint, nullptr, traversability_default, npaths, path_begin, poses_xy, is_safe, traversability, memory);
+}
+
+int te_check_footprint_paths2(te_ctx* c, const te_geometry* g, const float* footprint, const float* robot_slope, double traversability_default,
+                              int32_t npaths, const int32_t* path_begin, const double* poses_xy, uint8_t* is_safe, double* traversability,
+                              int memory) {
   TE_ENTER(c);
   if (int rc = check_geometry(g)) return rc;
   if (!footprint) return fail(TE_ERR_MISSING_LAYER, "layer traversability_footprint is missing");
@@ -813,7 +833,7 @@ int te_check_footprint_paths(te_ctx* c, const te_geometry* g, const float* footp
   const te_slab s{0, g->cols, 0, 0};
   const te::SlabView v = make_view(c, g, s);
   if (memory == TE_MEM_DEVICE) {
-    te::launch_check_paths(v, g, traversability_default, footprint, npaths, path_begin, poses_xy, is_safe, traversability, c->stream);
+    te::launch_check_paths(v, g, traversability_default, footprint, robot_slope, npaths, path_begin, poses_xy, is_safe, traversability, c->stream);
     return launch_check(c, "k_check_paths");
   }
   // host arguments: path_begin is readable here, so the pose count is known
@@ -826,9 +846,13 @@ int te_check_footprint_paths(te_ctx* c, const te_geometry* g, const float* footp
   TE_CUDA(c->stage[4].reserve((size_t)npaths));
   TE_CUDA(c->stage[5].reserve(sizeof(double) * (size_t)npaths));
   TE_CUDA(cudaMemcpyAsync(c->stage[0].p, footprint, lbytes, cudaMemcpyHostToDevice, c->stream));
+  if (robot_slope) {
+    TE_CUDA(c->stage[3].reserve(lbytes));
+    TE_CUDA(cudaMemcpyAsync(c->stage[3].p, robot_slope, lbytes, cudaMemcpyHostToDevice, c->stream));
+  }
   TE_CUDA(cudaMemcpyAsync(c->stage[1].p, path_begin, sizeof(int32_t) * (size_t)(npaths + 1), cudaMemcpyHostToDevice, c->stream));
   TE_CUDA(cudaMemcpyAsync(c->stage[2].p, poses_xy, sizeof(double) * 2 * (size_t)nposes, cudaMemcpyHostToDevice, c->stream));
-  te::launch_check_paths(v, g, traversability_default, (const float*)c->stage[0].p, npaths, (const int*)c->stage[1].p,
+  te::launch_check_paths(v, g, traversability_default, (const float*)c->stage[0].p, robot_slope ? (const float*)c->stage[3].p : nullptr, npaths, (const int*)c->stage[1].p,
                          (const double*)c->stage[2].p, (unsigned char*)c->stage[4].p, (double*)c->stage[5].p, c->stream);
   if (int rc = launch_check(c, "k_check_paths")) return rc;
   TE_CUDA(cudaMemcpyAsync(is_safe, c->stage[4].p, (size_t)npaths, cudaMemcpyDeviceToHost, c->stream));

@@ -7,6 +7,8 @@
 // replays the reference's own operand order on absolute coordinates) only where even that cannot
 // decide: numerically rank-deficient scatter matrices (the reference's FullPivHouseholderQR rank
 // test), ill-conditioned eigenvectors, or n_z within 1e-9 of a float32 rounding boundary.
+#include <algorithm>
+
 #include "te_fused.h"
 
 namespace te {
@@ -282,6 +284,8 @@ __device__ bool normals_t2(const FixupArgs& A, const Elev& E, int i, int j, floa
 __global__ void __launch_bounds__(128, 8) k_fixup_t2(FixupArgs A, const float* __restrict__ elev, ChainOut o,
                                                   const unsigned* __restrict__ list, const unsigned* __restrict__ count,
                                                   unsigned cap, unsigned* list3, unsigned* count3, unsigned cap3) {
+  asm volatile("griddepcontrol.launch_dependents;");   // tier 3 may be set up while this grid runs
+  asm volatile("griddepcontrol.wait;" ::: "memory");   // programmatic dependent launch: the fused kernel has finished and flushed its list
   unsigned n = *count;
   if (n > cap) n = cap;
   for (unsigned k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
@@ -330,8 +334,20 @@ __global__ void __launch_bounds__(128, 8) k_fixup_t2(FixupArgs A, const float* _
 }  // namespace
 
 void launch_fixup_t2(const FixupArgs& a, const float* elev, const ChainOut& o, const unsigned* list, const unsigned* count,
-                     unsigned cap, unsigned* list3, unsigned* count3, unsigned cap3, int sms, cudaStream_t s) {
-  k_fixup_t2<<<sms * 64, 128, 0, s>>>(a, elev, o, list, count, cap, list3, count3, cap3);  // ~1.2 M threads: one listed cell each, latency hidden by occupancy
+                     unsigned cap, unsigned* list3, unsigned* count3, unsigned cap3, int sms, cudaStream_t s, bool pdl) {
+  cudaLaunchConfig_t cfg{};
+  // one listed cell per thread up to ~1.2 M threads (latency hidden by occupancy), grid-stride beyond; small launches get a grid in
+  // proportion to their cell count (about 3 % of the cells are listed) so that a 2048^2 map does not pay for 9 472 blocks
+  const unsigned long long want = ((unsigned long long)cap3 / 32ull + 127ull) / 128ull;  // cap3 = cells of the launch (all maps)
+  cfg.gridDim = dim3((unsigned)std::min<unsigned long long>((unsigned long long)sms * 64ull, std::max<unsigned long long>(want, (unsigned long long)sms * 2ull)));
+  cfg.blockDim = dim3(128);
+  cfg.stream = s;
+  cudaLaunchAttribute at{};
+  at.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at.val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = &at;
+  cfg.numAttrs = pdl ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, k_fixup_t2, a, elev, o, list, count, cap, list3, count3, cap3);
 }
 
 }  // namespace te

@@ -345,37 +345,18 @@ __global__ void __launch_bounds__(256) k_sweep(FpArgs A, Layers L, const unsigne
   }
 }
 
-// One warp per input-buffer column: prefix sums of t' = finite(traversability) ? value : default along the row
-// index (double; exact for float32 terms, so the order of summation does not matter) and packed blocked flags.
-__global__ void __launch_bounds__(256) k_fp_prepare(FpArgs A, Layers L, const unsigned char* __restrict__ blocked, double* __restrict__ P,
-                                                    unsigned* __restrict__ bits) {
+// One warp per input-buffer column: the blocked flags packed 32 rows per word (the tiled sweep's early outs and k_fp_nearest
+// read them; the prefix sums of t' are built per tile in shared memory by k_sweep_tile).
+__global__ void __launch_bounds__(256) k_fp_prepare(FpArgs A, const unsigned char* __restrict__ blocked, unsigned* __restrict__ bits) {
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
   for (int lb = warp; lb < A.in_ncols; lb += nwarps) {
-    const float* tcol = L.trav + (size_t)lb * A.rows;
     const unsigned char* bcol = blocked + (size_t)lb * A.rows;
-    double* pcol = P + (size_t)lb * (A.rows + 1);
     unsigned* wcol = bits + (size_t)lb * A.words;
-    double carry = 0.0;
-    if (lane == 0) pcol[0] = 0.0;
     for (int base = 0; base < A.rows; base += 32) {
       const int i = base + lane;
-      double v = 0.0;
-      bool b = false;
-      if (i < A.rows) {
-        const float t = __ldg(tcol + i);
-        v = finitef(t) ? (double)t : A.tdefault;
-        b = bcol[i] != 0;
-      }
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        const double o = __shfl_up_sync(0xffffffffu, v, d);
-        if (lane >= d) v += o;
-      }
-      if (i < A.rows) pcol[i + 1] = carry + v;
-      const unsigned w = __ballot_sync(0xffffffffu, b);
+      const unsigned w = __ballot_sync(0xffffffffu, i < A.rows && bcol[i] != 0);
       if (lane == 0) wcol[base >> 5] = w;
-      carry += __shfl_sync(0xffffffffu, v, 31);
     }
   }
 }
@@ -403,119 +384,197 @@ __global__ void __launch_bounds__(256) k_fp_nearest(FpArgs A, unsigned char* __r
   }
 }
 
-// isTraversable for every cell on prefix sums: the visited set is a lattice disk, so "is anything blocked in it"
-// and "sum / count of the visited cells" are 2L+1 column queries instead of ~pi r^2 visits; only when a blocker
-// exists is the ring that holds the first one walked in SpiralIterator order.
-__global__ void __launch_bounds__(256) k_sweep_fast(FpArgs A, Layers L, const unsigned char* __restrict__ blocked, float* __restrict__ out) {
-  const int W = 2 * A.L + 1;
-  // one block = 256 consecutive rows of ONE output column (blockIdx.y): a warp's centres share their column, so everything that
-  // depends only on the column — which disk columns exist, whether any blocked cell lies near the warp at all — is warp-uniform
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  const int j = A.out_col0 + (int)blockIdx.y;
-  {
-    const int lane = threadIdx.x & 31, i0 = i - lane;
-    if (i0 >= A.rows) return;  // whole warp beyond the last row
-    const bool active = i < A.rows;
-    const size_t c = (size_t)blockIdx.y * A.rows + (active ? i : 0);
-    const double cx = A.X[active ? i : 0], cy = A.Y[j];
-    // disk columns that exist in the map and in this slab's buffer
-    const int l_lo = max(-A.L, max(-j, A.in_col0 - j)), l_hi = min(A.L, min(A.cols_total - 1 - j, A.in_col0 + A.in_ncols - 1 - j));
-    // ---- warp-wide early out: is any cell blocked in the box of rows [i0 - L, i0 + 31 + L] x disk columns?  (packed flags,
-    //      a few words per column, shared by the 32 centres)  Mostly not: then no lane has anything to look for.
-    bool warp_any;
-    {
-      const int w0 = max(i0 - A.L, 0) >> 5, w1 = min(i0 + 31 + A.L, A.rows - 1) >> 5, nw = w1 - w0 + 1;
-      const int ne = (l_hi - l_lo + 1) * nw;
-      unsigned acc = 0;
-      for (int e = lane; e < ne; e += 32) {
-        const int l = l_lo + e / nw, w = w0 + e % nw;
-        acc |= __ldg(A.bits + (size_t)(j + l - A.in_col0) * A.words + w);
+// isTraversable for every cell on prefix sums: the visited set is a lattice disk, so "is anything blocked in it" and "sum / count
+// of the visited cells" are 2L+1 column queries instead of ~pi r^2 visits; only when a blocker exists is the ring that holds the
+// first one walked in SpiralIterator order.
+// The sweep, tiled: a CTA owns TR x TC centres and stages what their disks touch — the column prefix sums of t' over the tile's
+// rows plus L rows of halo, for the tile's columns plus L columns of halo — in shared memory, computing them in place from the
+// traversability layer (prefix sums local to the tile: small magnitudes, no 8-byte-per-cell array in HBM).  k_sweep_fast sends
+// 2(2L+1) 8-byte loads per centre to L1/L2 (12 GB of L2 traffic at 4096^2, r = 0.45 m: that, not HBM, bounds it); here they are
+// conflict-free LDS.64 (lanes = consecutive rows).  Cells outside the map or the slab's buffer contribute 0 to a prefix sum, so
+// sums need no clipping — only the cell count of a centre near the border does.
+constexpr int TR = 64, TC = 32;
+static_assert(TR + 2 * 31 <= 128, "k_sweep_tile scans a staged column (TR + 2L rows, L <= 31) in one pass of 4 rows per lane");
+__global__ void __launch_bounds__(256) k_sweep_tile(FpArgs A, Layers L, const unsigned char* __restrict__ blocked, float* __restrict__ out) {
+  extern __shared__ double sP[];  // [NC][PS]: sP[c][k] = sum of t' over staged rows [0, k) of staged column c
+  const int Lr = A.L, NR = TR + 2 * Lr, NC = TC + 2 * Lr, PS = NR + 1, W = 2 * Lr + 1;
+  unsigned char* sNear = reinterpret_cast<unsigned char*>(sP + (size_t)NC * PS);  // [NC][TR]: nearest-blocked bytes of the centre rows
+  unsigned char* sBlk = sNear + (size_t)NC * TR;                                   // [NC][128]: blocked flag of every staged cell
+  const int r0 = (int)blockIdx.x * TR, c0 = A.out_col0 + (int)blockIdx.y * TC;
+  const int rb = r0 - Lr, cb = c0 - Lr;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  auto tprime = [&](int a, int b) { const double* q = sP + (size_t)(b - cb) * PS + (a - rb); return q[1] - q[0]; };  // one float32 term: exact
+  // ---- phase 1: prefix sums (one warp per staged column, lanes along the rows) and "is anything blocked near this tile"
+  int anyb = 0;
+  for (int cc = warp; cc < NC; cc += 8) {
+    const int gcol = cb + cc, lb = gcol - A.in_col0;
+    const bool col_ok = gcol >= 0 && gcol < A.cols_total && lb >= 0 && lb < A.in_ncols;
+    const float* tcol = L.trav + (size_t)(col_ok ? lb : 0) * A.rows;
+    const unsigned char* bcol = blocked + (size_t)(col_ok ? lb : 0) * A.rows;
+    double* pcol = sP + (size_t)cc * PS;
+    // NR <= 4 * 32 (L <= 31): a lane takes four consecutive rows, scans them in registers, the warp scans the lane totals
+    double v[4];
+    unsigned bw = 0;
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+      const int k = 4 * lane + m, row = rb + k;
+      v[m] = 0.0;
+      if (k < NR && col_ok && row >= 0 && row < A.rows) {
+        const float t = __ldg(tcol + row);
+        v[m] = finitef(t) ? (double)t : A.tdefault;
+        bw |= (unsigned)(bcol[row] != 0) << (8 * m);
       }
-      warp_any = __any_sync(0xffffffffu, acc != 0u);
     }
-    if (!active) return;
-    // ---- nearest blocked cell of the visited set, as a squared index distance ------------------------
+    anyb |= (int)bw;
+    reinterpret_cast<unsigned*>(sBlk)[cc * 32 + lane] = bw;
+    v[1] += v[0]; v[2] += v[1]; v[3] += v[2];
+    double tot = v[3];
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const double o = __shfl_up_sync(0xffffffffu, tot, d);
+      if (lane >= d) tot += o;
+    }
+    double before = __shfl_up_sync(0xffffffffu, tot, 1);  // sum of the rows held by the lanes below
+    if (lane == 0) before = 0.0;
+    if (lane == 0) pcol[0] = 0.0;
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+      const int k = 4 * lane + m;
+      if (k < NR) pcol[k + 1] = before + v[m];
+    }
+  }
+  const bool tile_any = __syncthreads_or(anyb) != 0;
+  if (tile_any) {  // the tile's rows of the nearest-blocked bytes, every staged column (TR = 64 bytes per column: 16 words)
+    for (int e = threadIdx.x; e < NC * (TR / 4); e += blockDim.x) {
+      const int cc = e / (TR / 4), w = e % (TR / 4);
+      const int gcol = cb + cc, lb = gcol - A.in_col0, row = r0 + 4 * w;
+      unsigned v = 0xffffffffu;  // 255: nothing blocked within reach
+      if (gcol >= 0 && gcol < A.cols_total && lb >= 0 && lb < A.in_ncols) {
+        const unsigned char* src = A.near + (size_t)lb * A.rows + row;
+        if (row + 3 < A.rows && ((size_t)src & 3u) == 0) v = __ldg(reinterpret_cast<const unsigned*>(src));
+        else {
+          v = 0;
+          for (int m = 0; m < 4; ++m) v |= (unsigned)((row + m < A.rows) ? __ldg(src + m) : 255u) << (8 * m);
+        }
+      }
+      reinterpret_cast<unsigned*>(sNear)[cc * (TR / 4) + w] = v;
+    }
+    __syncthreads();
+  }
+  // ---- phase 2: centres.  A warp is 32 consecutive rows of one column at a time (8 columns per warp).
+  const int i = r0 + (warp & 1) * 32 + lane;
+  const int i0 = i - lane;
+  if (i0 >= A.rows) return;
+  const bool active = i < A.rows;
+  const double cx = A.X[active ? i : 0];
+  const int k0 = i - rb;  // centre's staged row
+  // One bit per buffer column the warp's centres can reach: "a cell of rows [i0 - L, i0 + 31 + L] of this column is blocked" (from
+  // the packed flags; one pass for all TC/4 centres of the warp).  A centre whose disk columns are all clear has nothing to look for.
+  unsigned long long cm0 = 0ull, cm1 = 0ull;
+  int ca = 0;
+  if (tile_any) {
+    const int ja = c0 + (warp >> 1) * (TC / 4), jb = min(ja + TC / 4 - 1, A.out_col0 + A.out_ncols - 1);
+    ca = max(ja - Lr, max(0, A.in_col0));
+    const int cz = min(jb + Lr, min(A.cols_total - 1, A.in_col0 + A.in_ncols - 1));
+    const int w0 = max(i0 - Lr, 0) >> 5, w1 = min(i0 + 31 + Lr, A.rows - 1) >> 5;
+    for (int e0 = 0; e0 <= cz - ca; e0 += 32) {
+      unsigned acc = 0;
+      if (e0 + lane <= cz - ca) {
+        const unsigned* wc = A.bits + (size_t)(ca + e0 + lane - A.in_col0) * A.words;
+        for (int w = w0; w <= w1; ++w) acc |= __ldg(wc + w);
+      }
+      const unsigned long long bal = (unsigned long long)__ballot_sync(0xffffffffu, acc != 0u);
+      if (e0 < 64) cm0 |= bal << e0; else cm1 |= bal << (e0 - 64);
+    }
+  }
+  for (int q = 0; q < TC / 4; ++q) {
+    const int j = c0 + (warp >> 1) * (TC / 4) + q;
+    if (j >= A.out_col0 + A.out_ncols) break;
+    const size_t c = (size_t)(j - A.out_col0) * A.rows + (active ? i : 0);
+    const double cy = A.Y[j];
+    const int l_lo = max(-Lr, max(-j, A.in_col0 - j)), l_hi = min(Lr, min(A.cols_total - 1 - j, A.in_col0 + A.in_ncols - 1 - j));
+    bool warp_any = false;
+    if (tile_any) {
+      const int s0 = j + l_lo - ca, cnt = l_hi - l_lo + 1;  // cnt <= 63, bits [s0, s0 + cnt) of the 128-bit mask
+      unsigned long long m = s0 < 64 ? (cm0 >> s0) : (cm1 >> (s0 - 64));
+      if (s0 > 0 && s0 < 64) m |= cm1 << (64 - s0);
+      warp_any = (m & ((1ull << cnt) - 1ull)) != 0ull;
+    }
+    if (!active) continue;
     int best = 0x7fffffff;
     if (warp_any) {
-      const unsigned char* nr = A.near + (size_t)(j + l_lo - A.in_col0) * A.rows + i;
-      for (int l = l_lo; l <= l_hi; ++l, nr += A.rows) {
-        const int g = (int)__ldg(nr);              // nearest blocked row offset in this column
-        const int hw = A.halfw_c[l + A.L];
+      const unsigned char* nr = sNear + (size_t)(j + l_lo - cb) * TR + (i - r0);
+      for (int l = l_lo; l <= l_hi; ++l, nr += TR) {
+        const int g = (int)*nr;
+        const int hw = A.halfw_c[l + Lr];
         if (g <= hw) best = min(best, g * g + l * l);
       }
-      for (int q = 0; q < A.n_fuzzy; ++q) {
-        const int w = A.fuzzy[q];
+      for (int f = 0; f < A.n_fuzzy; ++f) {
+        const int w = A.fuzzy[f];
         const int di = (int)(signed char)(w & 0xff), dj = (int)(signed char)((w >> 8) & 0xff);
         const int a = i + di, b = j + dj, lb = b - A.in_col0;
         if (a < 0 || b < 0 || a >= A.rows || b >= A.cols_total || lb < 0 || lb >= A.in_ncols) continue;
         const double dx = A.X[a] - cx, dy = A.Y[b] - cy;
         if (!(dx * dx + dy * dy <= A.rmax2)) continue;
-        if (blocked[(size_t)lb * A.rows + a]) best = min(best, di * di + dj * dj);
+        if (sBlk[(b - cb) * 128 + (a - rb)]) best = min(best, di * di + dj * dj);
       }
     }
-    // ---- sums over the visited cells before the first blocked one --------------------------------------
     const bool any = best != 0x7fffffff;
-    const int dstar = any ? (int)sqrt((double)best) : A.nrings + 1;  // ring of the first blocked cell
-    const signed char* hwt = any ? (A.inner + (size_t)dstar * W) : A.halfw;
+    const int dstar = any ? (int)sqrt((double)best) : A.nrings + 1;
+    // The first blocked cell in visit order lies in ring dstar, so its index-space radius is in [dstar, dstar + 1) (exactly dstar
+    // with the integer norm): when that is within the inner radius the result is 0 (TraversabilityMap.cpp:694-704) whatever the
+    // sums are — most centres near an obstacle end here, without prefix sums or a ring walk.
+    if (any && (A.rmin == 0.0 || (A.int_norm ? (double)dstar : (double)(dstar + 1)) * A.res <= A.rmin)) {
+      out[c] = 0.0f;
+      continue;
+    }
+    const double* pc0 = sP + (size_t)(j - cb) * PS + k0;  // the centre's own prefix entry
+    const bool interior = i - Lr >= 0 && i + Lr < A.rows;
     double t = 0.0, t_b = 0.0;
     int n = 0;
-    if (!warp_any && i - A.L >= 0 && i + A.L < A.rows) {
-      // nothing blocked near this warp and no clipping along the rows: 2 loads and 2 additions per disk column, offsets from
-      // the constant bank
-      const double* pc0 = A.P + (size_t)(j - A.in_col0) * ((size_t)A.rows + 1) + i;
-      int l = l_lo + A.L;
-      const int l_end = l_hi + A.L;
-      for (; l + 1 <= l_end; l += 2) {
+    if (!any) {
+      // whole disk: offsets from the constant bank; columns that do not exist are all-zero prefix columns
+      int l = 0;
+      for (; l + 1 < W; l += 2) {
         t += pc0[A.off_hi[l]] - pc0[A.off_lo[l]];
         t_b += pc0[A.off_hi[l + 1]] - pc0[A.off_lo[l + 1]];
       }
-      if (l <= l_end) t += pc0[A.off_hi[l]] - pc0[A.off_lo[l]];
+      t += pc0[A.off_hi[l]] - pc0[A.off_lo[l]];
       t += t_b;
-      n = (int)A.cntp[l_end + 1] - (int)A.cntp[l_lo + A.L];
-    } else {
-      const double* pc = A.P + (size_t)(j + l_lo - A.in_col0) * (A.rows + 1);
-      const size_t pstride = (size_t)A.rows + 1;
-      if (i - A.L >= 0 && i + A.L < A.rows) {  // no clipping along the rows: two independent accumulators
-        int l = l_lo;
-        for (; l + 1 <= l_hi; l += 2, pc += 2 * pstride) {
-          const int h0 = hwt[l + A.L], h1 = hwt[l + 1 + A.L];
-          if (h0 >= 0) { t += pc[i + h0 + 1] - pc[i - h0]; n += 2 * h0 + 1; }
-          if (h1 >= 0) { t_b += pc[pstride + i + h1 + 1] - pc[pstride + i - h1]; n += 2 * h1 + 1; }
-        }
-        if (l <= l_hi) {
-          const int h0 = hwt[l + A.L];
-          if (h0 >= 0) { t += pc[i + h0 + 1] - pc[i - h0]; n += 2 * h0 + 1; }
-        }
+      if (interior) {
+        n = (int)A.cntp[l_hi + Lr + 1] - (int)A.cntp[l_lo + Lr];
       } else {
-        for (int l = l_lo; l <= l_hi; ++l, pc += pstride) {
-          const int hw = hwt[l + A.L];
-          if (hw < 0) continue;
-          const int a0 = max(i - hw, 0), a1 = min(i + hw, A.rows - 1);
-          t += pc[a1 + 1] - pc[a0];
-          n += a1 - a0 + 1;
+        for (int l2 = l_lo; l2 <= l_hi; ++l2) {
+          const int hw = A.halfw_c[l2 + Lr];
+          if (hw >= 0) n += min(i + hw, A.rows - 1) - max(i - hw, 0) + 1;
         }
       }
-      t += t_b;
+    } else {
+      const signed char* hwt = A.inner + (size_t)dstar * W;
+      for (int l = l_lo; l <= l_hi; ++l) {
+        const int hw = hwt[l + Lr];
+        if (hw < 0) continue;
+        t += pc0[l * PS + hw + 1] - pc0[l * PS - hw];
+        n += min(i + hw, A.rows - 1) - max(i - hw, 0) + 1;
+      }
     }
     float result;
     if (!any) {
-      for (int q = 0; q < A.n_fuzzy; ++q) {  // on-circle cells belong to the last ring: they are visited last
-        const int w = A.fuzzy[q];
+      for (int f = 0; f < A.n_fuzzy; ++f) {  // on-circle cells belong to the last ring: they are visited last
+        const int w = A.fuzzy[f];
         const int di = (int)(signed char)(w & 0xff), dj = (int)(signed char)((w >> 8) & 0xff);
         const int a = i + di, b = j + dj, lb = b - A.in_col0;
         if (a < 0 || b < 0 || a >= A.rows || b >= A.cols_total || lb < 0 || lb >= A.in_ncols) continue;
         const double dx = A.X[a] - cx, dy = A.Y[b] - cy;
         if (!(dx * dx + dy * dy <= A.rmax2)) continue;
-        const float v = __ldg(L.trav + (size_t)lb * A.rows + a);
-        t += finitef(v) ? (double)v : A.tdefault;
+        t += tprime(a, b);
         ++n;
       }
       t /= (double)n;
       result = (float)t;
     } else {
-      // walk ring dstar in visit order up to its first blocked cell
       int di = 0, dj = 0;
-      for (int k = A.ring_start[dstar]; k < A.ring_start[dstar + 1]; ++k) {
+      for (int k = A.ring_start[dstar]; k < A.ring_start[dstar + 1]; ++k) {  // ring dstar in visit order up to its first blocked cell
         const int w = __ldg(A.spiral + k);
         di = (int)(signed char)(w & 0xff);
         dj = (int)(signed char)((w >> 8) & 0xff);
@@ -525,10 +584,8 @@ __global__ void __launch_bounds__(256) k_sweep_fast(FpArgs A, Layers L, const un
           const double dx = A.X[a] - cx, dy = A.Y[b] - cy;
           if (!(dx * dx + dy * dy <= A.rmax2)) continue;
         }
-        const size_t cc = (size_t)lb * A.rows + a;
-        if (blocked[cc]) break;
-        const float v = __ldg(L.trav + cc);
-        t += finitef(v) ? (double)v : A.tdefault;
+        if (sBlk[(b - cb) * 128 + (a - rb)]) break;
+        t += tprime(a, b);
         ++n;
       }
       const int d2 = di * di + dj * dj;
@@ -549,7 +606,7 @@ __global__ void __launch_bounds__(256) k_sweep_fast(FpArgs A, Layers L, const un
 // TraversabilityMap::checkCircularFootprintPath (TraversabilityMap.cpp:345-462) for a batch of paths — one thread per path — on a
 // traversability_footprint layer that is valid everywhere: every isTraversable(center, ...) takes the memoised branch
 // (:667-673), centres outside the map the default branch (:660-666).  No inclination check, no polygons.
-__global__ void __launch_bounds__(128) k_check_paths(FpArgs A, const float* __restrict__ fp, int npaths, const int* __restrict__ path_begin,
+__global__ void __launch_bounds__(128) k_check_paths(FpArgs A, const float* __restrict__ fp, const float* __restrict__ rslope, int npaths, const int* __restrict__ path_begin,
                                                      const double* __restrict__ xy, unsigned char* __restrict__ is_safe,
                                                      double* __restrict__ trav_out) {
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
@@ -567,17 +624,43 @@ __global__ void __launch_bounds__(128) k_check_paths(FpArgs A, const float* __re
     t = (double)lay(A, fp, i, j);
     return t != 0.0;
   };
+  // TraversabilityMap::checkInclination (TraversabilityMap.cpp:748-762) on the robot_slope layer; rslope == nullptr: check off
+  auto inclination_ok = [&](double ax, double ay, double bx, double by) -> bool {
+    if (!rslope) return true;
+    int si, sj, ei, ej;
+    if (bx == ax && by == ay) {
+      if (!is_inside_d(A, ax, ay) || !get_index_d(A, ax, ay, si, sj)) return false;
+      return !(lay(A, rslope, si, sj) == 0.0f);
+    }
+    if (!get_index_d(A, ax, ay, si, sj) || !get_index_d(A, bx, by, ei, ej)) return false;
+    const int dx = abs(ei - si), dy = abs(ej - sj);
+    int i1x = (ei >= si) ? 1 : -1, i2x = i1x, i1y = (ej >= sj) ? 1 : -1, i2y = i1y;
+    int den, num, numAdd, nCells;
+    if (dx >= dy) { i1x = 0; i2y = 0; den = dx; num = dx / 2; numAdd = dy; nCells = dx + 1; }
+    else { i2x = 0; i1y = 0; den = dy; num = dy / 2; numAdd = dx; nCells = dy + 1; }
+    int li = si, lj = sj;
+    for (int c = 0; c < nCells; ++c) {
+      const float v = lay(A, rslope, li, lj);
+      if (finitef(v) && v == 0.0f) return false;
+      num += numAdd;
+      if (num >= den) { num -= den; li += i1x; lj += i1y; }
+      li += i2x; lj += i2y;
+    }
+    return true;
+  };
   double result = 0.0, lengthPath = 0.0;
   double sx = 0.0, sy = 0.0, ex = 0.0, ey = 0.0;
   for (int k = 0; k < n; ++k) {
     sx = ex; sy = ey;
     ex = xy[2 * (b + k)]; ey = xy[2 * (b + k) + 1];
     if (n == 1) {
+      if (!inclination_ok(ex, ey, ex, ey)) return;
       double t;
       if (!circle(ex, ey, t)) return;
       result = t;
     }
     if (n > 1 && k > 0) {
+      if (!inclination_ok(sx, sy, ex, ey)) return;
       int si, sj, ei, ej;
       if (!get_index_d(A, sx, sy, si, sj) || !get_index_d(A, ex, ey, ei, ej)) return;
       // LineIterator (Bresenham) from the end index to the start index, every fourth cell checked
@@ -653,7 +736,7 @@ void FootprintState::release() {
   valid = false;
 }
 
-void launch_check_paths(const SlabView& v, const te_geometry* g, double traversability_default, const float* footprint, int npaths,
+void launch_check_paths(const SlabView& v, const te_geometry* g, double traversability_default, const float* footprint, const float* robot_slope, int npaths,
                         const int* path_begin, const double* xy, unsigned char* is_safe, double* trav, cudaStream_t s) {
   FpArgs a{};
   a.rows = v.rows; a.cols_total = v.cols_total; a.in_col0 = v.in_col0; a.in_ncols = v.in_ncols;
@@ -661,7 +744,7 @@ void launch_check_paths(const SlabView& v, const te_geometry* g, double traversa
   a.res = g->resolution; a.lenx = g->length_x; a.leny = g->length_y; a.posx = g->position_x; a.posy = g->position_y;
   a.X = v.X; a.Y = v.Y;
   a.tdefault = traversability_default;
-  k_check_paths<<<(npaths + 127) / 128, 128, 0, s>>>(a, footprint, npaths, path_begin, xy, is_safe, trav);
+  k_check_paths<<<(npaths + 127) / 128, 128, 0, s>>>(a, footprint, robot_slope, npaths, path_begin, xy, is_safe, trav);
 }
 
 int footprint_halo(const te_geometry* g, const te_footprint_params* p) {
@@ -802,25 +885,25 @@ int launch_footprint(FootprintState& st, const SlabView& v, const te_geometry* g
     st.tables_valid = true;
   }
   const int words = (v.rows + 31) / 32;
-  const size_t pbytes = sizeof(double) * (size_t)(v.rows + 1) * v.in_ncols, wbytes = (sizeof(unsigned) * (size_t)words * v.in_ncols + 15) / 16 * 16;
+  const size_t wbytes = (sizeof(unsigned) * (size_t)words * v.in_ncols + 15) / 16 * 16;
   const size_t gbytes = ncell_in;
-  if (st.prefix_cap < pbytes + wbytes + gbytes) {
+  if (st.prefix_cap < wbytes + gbytes) {
     if (st.d_prefix) cudaFree(st.d_prefix);
     st.d_prefix = nullptr; st.prefix_cap = 0;
-    if (cudaMalloc(&st.d_prefix, pbytes + wbytes + gbytes) != cudaSuccess) { st.why = "cudaMalloc(footprint prefix sums) failed"; return TE_ERR_CUDA; }
-    st.prefix_cap = pbytes + wbytes + gbytes;
+    if (cudaMalloc(&st.d_prefix, wbytes + gbytes) != cudaSuccess) { st.why = "cudaMalloc(footprint flag words) failed"; return TE_ERR_CUDA; }
+    st.prefix_cap = wbytes + gbytes;
   }
   a.L = st.L; a.nrings = st.nrings; a.n_fuzzy = st.n_fuzzy; a.words = words;
   a.ring_start = (const int*)((char*)st.d_tables + st.off_ring);
   a.fuzzy = (const int*)((char*)st.d_tables + st.off_fuzzy);
   a.halfw = (const signed char*)((char*)st.d_tables + st.off_halfw);
   a.inner = (const signed char*)((char*)st.d_tables + st.off_inner);
-  a.P = (const double*)st.d_prefix;
-  a.bits = (const unsigned*)((char*)st.d_prefix + pbytes);
-  a.near = (const unsigned char*)st.d_prefix + pbytes + wbytes;
+  a.P = nullptr;
+  a.bits = (const unsigned*)st.d_prefix;
+  a.near = (const unsigned char*)st.d_prefix + wbytes;
   std::memcpy(a.halfw_c, st.h_halfw, sizeof(a.halfw_c));
+  const int pstride = TR + 2 * st.L + 1;  // pitch of a staged prefix-sum column in k_sweep_tile
   {
-    const int pstride = v.rows + 1;
     a.cntp[0] = 0;
     for (int k = 0; k < 64; ++k) {
       const int l = k - st.L, h = (k <= 2 * st.L) ? (int)st.h_halfw[k] : -1;
@@ -831,9 +914,16 @@ int launch_footprint(FootprintState& st, const SlabView& v, const te_geometry* g
   }
   const int g3 = std::min(sms * 8, (v.in_ncols + 7) / 8);
   const int g1b = (int)std::min<long long>((t1 + 255) / 256, (long long)sms * 8);
-  k_fp_prepare<<<std::max(g3, 1), 256, 0, s>>>(a, L, (const unsigned char*)st.d_block, (double*)st.d_prefix, (unsigned*)((char*)st.d_prefix + pbytes));
-  k_fp_nearest<<<std::max(g1b, 1), 256, 0, s>>>(a, (unsigned char*)st.d_prefix + pbytes + wbytes);
-  k_sweep_fast<<<dim3((unsigned)((v.rows + 255) / 256), (unsigned)v.out_ncols), 256, 0, s>>>(a, L, (const unsigned char*)st.d_block, out);
+  k_fp_prepare<<<std::max(g3, 1), 256, 0, s>>>(a, (const unsigned char*)st.d_block, (unsigned*)st.d_prefix);
+  k_fp_nearest<<<std::max(g1b, 1), 256, 0, s>>>(a, (unsigned char*)st.d_prefix + wbytes);
+  const size_t smem = sizeof(double) * (size_t)(TC + 2 * st.L) * pstride + (size_t)(TC + 2 * st.L) * (TR + 128);
+  if (!st.tile_attr) {
+    if (cudaFuncSetAttribute(k_sweep_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * (TC + 62) * (TR + 63) + (TC + 62) * (TR + 128))) != cudaSuccess) {
+      st.why = "cudaFuncSetAttribute(max dynamic shared memory) failed"; return TE_ERR_CUDA;
+    }
+    st.tile_attr = true;
+  }
+  k_sweep_tile<<<dim3((unsigned)((v.rows + TR - 1) / TR), (unsigned)((v.out_ncols + TC - 1) / TC)), 256, smem, s>>>(a, L, (const unsigned char*)st.d_block, out);
   if (launches) *launches = 5;
   return 0;
 }

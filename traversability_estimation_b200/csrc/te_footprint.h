@@ -25,8 +25,9 @@ struct FootprintState {
   size_t off_ring = 0, off_fuzzy = 0, off_halfw = 0, off_inner = 0;
   int n_fuzzy = 0, L = 0, nrings = 0;
   signed char h_halfw[64] = {0};
-  void* d_prefix = nullptr;
+  void* d_prefix = nullptr;   // packed blocked flags + nearest-blocked bytes (the prefix sums live in k_sweep_tile's shared memory)
   size_t prefix_cap = 0;
+  bool tile_attr = false;     // k_sweep_tile's dynamic shared-memory limit has been raised (a per-device function attribute)
   void* d_list = nullptr;    // work list of the cells whose predicates need the window / gap-walk code (word 0: length)
   size_t list_cap = 0;
   void invalidate() { valid = false; tables_valid = false; }
@@ -41,7 +42,7 @@ int launch_footprint(FootprintState& st, const SlabView& v, const te_geometry* g
                      float* rough_fp, int sms, cudaStream_t s, int* launches);
 
 // TraversabilityMap::checkCircularFootprintPath for a batch of paths on a complete traversability_footprint layer (device pointers).
-void launch_check_paths(const SlabView& v, const te_geometry* g, double traversability_default, const float* footprint, int npaths,
+void launch_check_paths(const SlabView& v, const te_geometry* g, double traversability_default, const float* footprint, const float* robot_slope, int npaths,
                         const int* path_begin, const double* xy, unsigned char* is_safe, double* trav, cudaStream_t s);
 
 }  // namespace te

@@ -797,6 +797,7 @@ __global__ void TE_KERNEL_ATTR k_chain_fused(const __grid_constant__ CUtensorMap
   }
   __syncwarp();
 
+  asm volatile("griddepcontrol.launch_dependents;");  // tier 2 (a programmatic dependent launch) may be set up while this grid runs
   const int total_warps = gridDim.x * WARPS_PER_CTA;
   const int gwarp = blockIdx.x * WARPS_PER_CTA + warp;
   const int nunits = A.lvl_unit0[NLVL];
@@ -946,7 +947,28 @@ void plan_levels(FusedArgs& a, int out_ncols, int nmaps, int total_warps) {
   int len[NLVL] = {len0, std::max(16, len0 * 3 / 8 / 8 * 8), 16, 16};
   double frac[NLVL] = {0.80, 0.15, 0.05, 0.0};
   if (len0 == 16) { frac[0] = 1.0; frac[1] = frac[2] = 0.0; }
-  const char* e = std::getenv("TE_FUSED_SEGS");  // calibration runs only: "len:frac,len:frac,..."
+  if (share < 100.0) {
+    // Small launches (a warp's share is a couple of units at most): the tapering queue has nothing to balance and the whole-unit
+    // quantisation decides — the kernel lasts rounds(len) units of len full march steps + 8 warm-up steps (which skip the later
+    // stages: ~0.45 of a step each) + ~4 steps of TMA pipeline fill, where rounds = ceil(units / warps).  Take the single segment
+    // length that minimises that (2048^2: 44 columns, one round, instead of 16 columns: three rounds; an 8192 x 1024 slab of the
+    // 8-GPU tiling: 88 columns, one round, instead of five rounds of 16).
+    int best_len = 16;
+    double best_cost = 1e300;
+    for (int l = 8; l <= 160; l += 4) {
+      const long long units = (long long)a.nstrips * ((out_ncols + l - 1) / l) * nmaps;
+      const long long rounds = (units + total_warps - 1) / total_warps;
+      const double cost = (double)rounds * (l + 8 * 0.45 + 4);
+      if (cost < best_cost - 1e-9) { best_cost = cost; best_len = l; }
+    }
+    len[0] = best_len;
+    frac[0] = 1.0; frac[1] = frac[2] = 0.0;
+  }
+#ifdef TE_CALIBRATION
+  const char* e = std::getenv("TE_FUSED_SEGS");  // calibration builds only (tools/dev_segs.sh): "len:frac,len:frac,..."
+#else
+  const char* e = nullptr;
+#endif
   if (e && *e) {
     for (int i = 0; i < NLVL; ++i) { len[i] = 16; frac[i] = 0.0; }
     int i = 0, l = 0, n = 0;

@@ -51,8 +51,9 @@ struct FixupArgs {
 
 // Fills the tier-2 arguments for the shape the fused stencil was found eligible for.
 void make_fixup_args(const FusedState& st, const SlabView& v, const ChainDev& p, FixupArgs* out);
+// pdl: launch as a programmatic dependent of the preceding kernel of the stream (the kernel waits on griddepcontrol.wait)
 void launch_fixup_t2(const FixupArgs& a, const float* elev, const ChainOut& o, const unsigned* list, const unsigned* count,
-                     unsigned cap, unsigned* list3, unsigned* count3, unsigned cap3, int sms, cudaStream_t s);
+                     unsigned cap, unsigned* list3, unsigned* count3, unsigned cap3, int sms, cudaStream_t s, bool pdl);
 
 // Work lists.  The fused kernel appends in warp-private chunks: entries equal to LIST_INVALID are padding and are skipped by the
 // consumers; count[0] = list entries reserved (chunks), count[1] = cells flagged, count[2] = overflow flag (never set when the

@@ -383,7 +383,10 @@ __global__ void __launch_bounds__(128) k_chain_generic(SlabView v, ChainDev p, c
 // Certified slow path of the fused stencil: recompute the listed cells (j_local*rows+i | flags<<30).
 __global__ void __launch_bounds__(128) k_fixup_cells(SlabView v, ChainDev p, const float* __restrict__ elev, ChainOut o,
                                                      const unsigned int* __restrict__ list,
-                                                     const unsigned int* __restrict__ count, unsigned int cap) {
+                                                     const unsigned int* __restrict__ count, unsigned int cap,
+                                                     unsigned int* __restrict__ zero_next) {
+  asm volatile("griddepcontrol.wait;" ::: "memory");  // programmatic dependent launch: tier 2 has finished and flushed its list
+  if (zero_next && blockIdx.x == 0) zero_next[threadIdx.x] = 0u;  // the counter block of the next chain call (blockDim.x == 128 words)
   unsigned int n = *count;
   if (n > cap) n = cap;
   // A literal cell is ~40 us of serial, branchy double-precision code (half of it instruction fetch).  The usual handful of cells gets one warp each
@@ -517,8 +520,17 @@ void launch_chain_generic(const SlabView& v, const ChainDev& p, const float* ele
 }
 
 void launch_fixup(const SlabView& v, const ChainDev& p, const float* elev, const ChainOut& o, const unsigned int* list,
-                  const unsigned int* count, unsigned int cap, int sms, cudaStream_t s) {
-  k_fixup_cells<<<sms * 4, 128, 0, s>>>(v, p, elev, o, list, count, cap);
+                  const unsigned int* count, unsigned int cap, unsigned int* zero_next, int sms, cudaStream_t s, bool pdl) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)(sms * 4));
+  cfg.blockDim = dim3(128);
+  cfg.stream = s;
+  cudaLaunchAttribute at{};
+  at.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at.val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = &at;
+  cfg.numAttrs = pdl ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, k_fixup_cells, v, p, elev, o, list, count, cap, zero_next);
 }
 
 void launch_normals(const SlabView& v, const ChainDev& p, const float* elev, float* nx, float* ny, float* nz, int sms, cudaStream_t s) {
