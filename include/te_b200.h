@@ -188,6 +188,20 @@ int te_footprint2(te_ctx* ctx, const te_geometry* g, const te_slab* slab, const 
                   const float* elevation, float* traversability_footprint, float* slope_footprint_or_null,
                   float* step_footprint_or_null, float* roughness_footprint_or_null, int memory);
 
+/* TraversabilityMap::traversabilityFootprint(double footprintYaw), TraversabilityMap.cpp:239-305 — what the reference's
+ * `traversability_footprint` service runs (TraversabilityEstimation.cpp:272-276): every cell gets the footprint polygon
+ * (footprint/footprint_polygon, robot_footprint_parameter.yaml:3; `polygon_xy` = npts vertices (x, y) in the footprint frame,
+ * 3..16) placed at its centre, unrotated -> layer traversability_x, rotated by footprint_yaw about z -> traversability_rot.  Each
+ * value is isTraversable(polygon, traversability) (:592-645): 0 when a cell inside the polygon (grid_map::PolygonIterator) fails
+ * isTraversableForFilters, else the mean of the traversability layer over those cells (traversability_default for invalid
+ * cells, and when the polygon covers no cell).  Uses p->traversability_default, max_gap_width, critical_step_height,
+ * verify_roughness (radius / offset are ignored).  Slab halo: te_footprint's predicate halo + the polygon's reach.
+ * TE_ERR_UNSUPPORTED for a polygon that reaches further than 31 cells from its centre. */
+int te_footprint_polygon(te_ctx* ctx, const te_geometry* g, const te_slab* slab, const te_footprint_params* p, int32_t npts,
+                         const double* polygon_xy, double footprint_yaw, const float* traversability, const float* slope,
+                         const float* step, const float* roughness_or_null, const float* elevation, float* traversability_x,
+                         float* traversability_rot, int memory);
+
 /* TraversabilityMap::checkFootprintPath for circular footprints — checkCircularFootprintPath, TraversabilityMap.cpp:345-462 —
  * for a BATCH of paths in one launch (one thread per path: the service callback of the reference checks one path per call;
  * planners and MPC roll-outs ask for hundreds).  It is evaluated on a complete traversability_footprint layer, i.e. the output

@@ -160,6 +160,22 @@ def footprint(g, fp, traversability, slope_l, step_l, elevation, nthreads=0, rou
     return out, sfp, stfp, rfp
 
 
+def footprint_polygon(g, fp, polygon_xy, yaw, traversability, slope_l, step_l, elevation, nthreads=0, roughness=None):
+    """TraversabilityMap::traversabilityFootprint(yaw): (traversability_x, traversability_rot) for the footprint polygon
+    `polygon_xy` (vertices (x, y) in the footprint frame)."""
+    t, s, st, e = (_layer(g, v) for v in (traversability, slope_l, step_l, elevation))
+    r = _layer(g, roughness) if roughness is not None else None
+    pts = np.ascontiguousarray(polygon_xy, dtype=np.float64).reshape(-1, 2)
+    ox, orot = _new(g), _new(g)
+    L = lib()
+    L.teo_footprint_polygon.argtypes = [C.POINTER(Geometry), C.POINTER(FootprintParams), C.c_int, C.c_void_p, C.c_double] + [C.c_void_p] * 7 + [C.c_int]
+    rc = L.teo_footprint_polygon(C.byref(g), C.byref(fp), len(pts), pts.ctypes.data, float(yaw), t.ctypes.data, s.ctypes.data,
+                                 st.ctypes.data, r.ctypes.data if r is not None else None, e.ctypes.data, ox.ctypes.data,
+                                 orot.ctypes.data, nthreads)
+    assert rc == 0, rc
+    return ox, orot
+
+
 def check_circular_paths(g, footprint_layer, traversability_default, path_begin, poses_xy, robot_slope=None):
     """(is_safe uint8[npaths], traversability float64[npaths]) of TraversabilityMap::checkCircularFootprintPath per path;
     robot_slope: the layer checkInclination reads when checkRobotInclination_ is set (None: off)."""

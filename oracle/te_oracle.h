@@ -94,6 +94,13 @@ int teo_footprint2(const teo_geometry* g, const teo_footprint_params* p, const f
                    const float* slope, const float* step, const float* roughness_or_null, const float* elevation,
                    float* out_footprint, float* slope_fp_or_null, float* step_fp_or_null, float* rough_fp_or_null, int nthreads);
 
+/* TraversabilityMap::traversabilityFootprint(double footprintYaw) (TraversabilityMap.cpp:239-305) with the polygon
+ * isTraversable (:592-645): layers traversability_x (footprint polygon at every cell centre, unrotated) and traversability_rot
+ * (rotated by yaw about z).  pts_xy: npts footprint vertices (x, y) in the footprint frame (robot_footprint_parameter.yaml:3). */
+int teo_footprint_polygon(const teo_geometry* g, const teo_footprint_params* p, int npts, const double* pts_xy, double yaw,
+                          const float* traversability, const float* slope, const float* step, const float* roughness_or_null,
+                          const float* elevation, float* out_traversability_x, float* out_traversability_rot, int nthreads);
+
 /* TraversabilityMap::checkCircularFootprintPath (TraversabilityMap.cpp:345-462) for a batch of paths on a
  * traversability_footprint layer that is valid everywhere (memoised isTraversable branch :667-673): path q is the poses
  * poses_xy[2*path_begin[q] .. 2*path_begin[q+1]).  Outputs TraversabilityResult.is_safe / .traversability per path. */

@@ -367,6 +367,107 @@ int teo_footprint2(const teo_geometry* g, const teo_footprint_params* p, const f
   return 0;
 }
 
+// grid_map::Polygon::isInside (grid_map_core Polygon.cpp, recalled): crossing-number test on the vertex list.
+static bool polygon_is_inside(const std::vector<V2>& v, V2 pt) {
+  int cross = 0;
+  for (size_t i = 0, j = v.size() - 1; i < v.size(); j = i++) {
+    if (((v[i].y > pt.y) != (v[j].y > pt.y)) &&
+        (pt.x < (v[j].x - v[i].x) * (pt.y - v[i].y) / (v[j].y - v[i].y) + v[i].x))
+      ++cross;
+  }
+  return (cross % 2) != 0;
+}
+
+// TraversabilityMap::traversabilityFootprint(double footprintYaw), TraversabilityMap.cpp:239-305: every cell gets the footprint
+// polygon (footprint/footprint_polygon, robot_footprint_parameter.yaml:3) placed at its centre, unrotated -> traversability_x and
+// rotated by footprintYaw about z -> traversability_rot, each evaluated by isTraversable(polygon, traversability) :592-645:
+// grid_map::PolygonIterator (bounding box of the vertices bound to the map — findSubmapParameters —, cells in SubmapIterator
+// order, Polygon::isInside on the cell centre) -> 0.0 as soon as a cell fails isTraversableForFilters (:601-611), otherwise the
+// mean of the traversability layer with traversabilityDefault_ for invalid cells (:612-619,:630), traversabilityDefault_ when the
+// polygon covers no cell (:625-628).  Vertices: `toPosition * orientation * positionToVertex` (:277-278) = Eigen
+// Translation * Quaternion -> Isometry transform (rotation MATRIX of the quaternion, Quaternion::toRotationMatrix) applied to the
+// point, restated in that operand order; the quaternion of kindr::AngleAxisD(yaw, 0, 0, 1) * identity is (cos(yaw/2), 0, 0, sin(yaw/2)).
+// PARITY UNPINNED like the rest of this file (PolygonIterator / Polygon recalled from grid_map 1.6.x, no reference data).
+int teo_footprint_polygon(const teo_geometry* g, const teo_footprint_params* p, int npts, const double* pts_xy, double yaw,
+                          const float* trav, const float* slope, const float* step, const float* rough, const float* elev,
+                          float* out_x, float* out_rot, int nthreads) {
+  if (!g || g->rows <= 0 || g->cols <= 0 || !(g->resolution > 0.0) || !p || npts < 3 || !pts_xy || !trav || !slope || !step || !elev ||
+      !out_x || !out_rot)
+    return 1;
+  if (p->verify_roughness && !rough) return 1;
+  Map m{g->rows, g->cols, g->resolution, {g->length_x, g->length_y}, {g->position_x, g->position_y}, trav, slope, step, elev, {}, {}};
+  m.X.resize(m.rows);
+  m.Y.resize(m.cols);
+  for (int i = 0; i < m.rows; ++i) m.X[i] = cell_coord(m.pos.x, m.len.x, m.res, i);
+  for (int j = 0; j < m.cols; ++j) m.Y[j] = cell_coord(m.pos.y, m.len.y, m.res, j);
+  int nt = 1;
+#ifdef _OPENMP
+  nt = nthreads > 0 ? nthreads : omp_get_max_threads();
+#else
+  (void)nthreads;
+#endif
+  (void)nt;
+  std::vector<unsigned char> blocked;
+  compute_blocked(m, *p, rough, blocked, nullptr, nullptr, nullptr, nt);
+  // rotation matrices (Eigen::Quaternion::toRotationMatrix with x = y = 0)
+  double R[2][2][2];
+  for (int which = 0; which < 2; ++which) {
+    const double w = which ? std::cos(0.5 * yaw) : 1.0, z = which ? std::sin(0.5 * yaw) : 0.0;
+    const double tz = 2.0 * z, twz = tz * w, tzz = tz * z;
+    R[which][0][0] = 1.0 - (0.0 + tzz); R[which][0][1] = 0.0 - twz;
+    R[which][1][0] = 0.0 + twz;         R[which][1][1] = 1.0 - (0.0 + tzz);
+  }
+#pragma omp parallel for schedule(dynamic, 4) num_threads(nt)
+  for (int j = 0; j < m.cols; ++j) {
+    std::vector<V2> poly(npts);
+    for (int i = 0; i < m.rows; ++i) {
+      const V2 pos{m.X[i], m.Y[j]};                                                   // :266 getPosition(*iterator, position)
+      for (int which = 0; which < 2; ++which) {
+        for (int k = 0; k < npts; ++k) {                                              // :273-290
+          const double px = pts_xy[2 * k], py = pts_xy[2 * k + 1];
+          const double rx = (R[which][0][0] * px + R[which][0][1] * py) + 0.0;        // linear() * v (the z column is zero)
+          const double ry = (R[which][1][0] * px + R[which][1][1] * py) + 0.0;
+          poly[k] = V2{pos.x + rx, pos.y + ry};                                       // + translation()
+        }
+        // PolygonIterator::findSubmapParameters
+        V2 topLeft = poly[0], bottomRight = poly[0];
+        for (const V2& q : poly) {
+          topLeft = V2{std::max(topLeft.x, q.x), std::max(topLeft.y, q.y)};
+          bottomRight = V2{std::min(bottomRight.x, q.x), std::min(bottomRight.y, q.y)};
+        }
+        bound_position(m, topLeft);
+        bound_position(m, bottomRight);
+        int si, sj, ei, ej;
+        get_index(m, topLeft, si, sj);
+        get_index(m, bottomRight, ei, ej);
+        unsigned nCells = 0;
+        double t = 0.0;
+        bool ok = true;
+        for (int a = si; a <= ei && ok; ++a)                                          // SubmapIterator: column index fastest
+          for (int b = sj; b <= ej; ++b) {
+            if (a < 0 || b < 0 || a >= m.rows || b >= m.cols) continue;
+            if (!polygon_is_inside(poly, V2{m.X[a], m.Y[b]})) continue;               // PolygonIterator::isInside
+            const size_t c = (size_t)b * m.rows + a;
+            if (blocked[c]) { ok = false; break; }                                    // :601-611 (computeUntraversablePolygon false)
+            ++nCells;                                                                 // :613
+            const float v = trav[c];
+            t += std::isfinite(v) ? (double)v : p->traversability_default;            // :614-618
+          }
+        float result;
+        if (!ok) {
+          result = 0.0f;                                                              // :297 / :301
+        } else if (nCells == 0) {
+          result = (float)p->traversability_default;                                  // :625-628 (0.0 either way when the default is 0)
+        } else {
+          result = (float)(t / nCells);                                               // :630, stored to a float layer :295,:299
+        }
+        (which ? out_rot : out_x)[(size_t)j * m.rows + i] = result;
+      }
+    }
+  }
+  return 0;
+}
+
 // TraversabilityMap::checkCircularFootprintPath, TraversabilityMap.cpp:345-462, for a batch of paths, evaluated on a
 // traversability_footprint layer that is valid everywhere (i.e. after traversabilityFootprint(radius, offset), :307-318): every
 // isTraversable(center, ...) then takes the memoised branch :667-673 (traversability = layer value, traversable = value != 0);

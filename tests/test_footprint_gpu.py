@@ -196,3 +196,30 @@ def test_batched_circular_footprint_paths(te, ctx, oracle):
     safe2, t2 = ctx.check_footprint_paths(g, fpl, fo.traversability_default, begin, poses, robot_slope=rs)
     assert np.array_equal(safe2, ref_safe2) and np.array_equal(t2, ref_t2)
     assert int(safe2.sum()) < int(safe.sum()) and not (safe2 & ~safe).any()
+
+
+@pytest.mark.parametrize("case", [
+    dict(rows=160, cols=140, seed=61, res=0.02, yaw=0.7854),          # YAML footprint + robot.yaml yaw: 92 on-edge offsets at 0.02 m
+    dict(rows=150, cols=133, seed=62, res=0.03, yaw=0.3, position=(57.25, -31.5)),
+    dict(rows=96, cols=200, seed=63, res=0.02, yaw=1.5707963267948966, poly=[[0.5, 0.2], [0.1, -0.3], [-0.5, -0.2], [-0.4, 0.26], [0.0, 0.1]]),
+])
+def test_polygon_footprint_sweep_matches_oracle(te, ctx, oracle, case):
+    """§8(f)-3: traversabilityFootprint(yaw) (TraversabilityMap.cpp:239-305, :592-645): traversability_x / traversability_rot."""
+    res, pos = case["res"], case.get("position", (0.0, 0.0))
+    poly = case.get("poly", [[0.45, 0.30], [0.45, -0.30], [-0.45, -0.30], [-0.45, 0.30]])   # robot_footprint_parameter.yaml:3
+    z = synth.terrain(case["rows"], case["cols"], res, case["seed"], "mixed", pos)
+    og = oracle.Geometry.make(case["rows"], case["cols"], res, pos)
+    g = te.Geometry.make(case["rows"], case["cols"], res, pos)
+    ch = oracle.chain(og, oracle.ChainParams.yaml_defaults(0), z)
+    fo, ft = oracle.FootprintParams.yaml_defaults(), te.FootprintParams.yaml_defaults()
+    layers = [np.asfortranarray(x, dtype=np.float32) for x in (ch["traversability"], ch["slope"], ch["step"], z)]
+    rx, rrot = oracle.footprint_polygon(og, fo, poly, case["yaw"], *layers)
+    ox, orot = np.empty_like(layers[0]), np.empty_like(layers[0])
+    ctx.footprint_polygon(g, ft, poly, case["yaw"], *layers, ox, orot, te.MEM_HOST)
+    for a, b, name in ((ox, rx, "traversability_x"), (orot, rrot, "traversability_rot")):
+        assert not np.isnan(a).any() and not np.isnan(b).any(), name
+        assert np.array_equal(a == 0, b == 0), (name, int(((a == 0) != (b == 0)).sum()))   # same cells blocked: same polygon membership
+        assert _close(a, b), (name, int((a != b).sum()), float(np.abs(a - b).max()))
+    assert (rx == 0).any() and (rx > 0).any() and (rrot > 0).any()
+    if case["yaw"] != 0.0:
+        assert not np.array_equal(rx, rrot)

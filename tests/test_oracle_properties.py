@@ -97,3 +97,29 @@ def test_check_inclination_in_path_check(oracle):
     rs4 = rs.copy(); rs4[20, 30] = np.nan; rs4[21, 30] = 0.0   # an invalid cell on the line is skipped, a zero next to the line is not seen
     assert oracle.check_circular_paths(g, fp, 0.3, begin, poses, robot_slope=rs4)[0].tolist() == [1, 1, 1]
     assert oracle.check_circular_paths(g, fp, 0.3, begin, poses)[0].tolist() == [1, 1, 1]   # check off
+
+
+def test_polygon_footprint_sweep_properties(oracle):
+    """traversabilityFootprint(yaw) (TraversabilityMap.cpp:239-305, polygon isTraversable :592-645) on a constant layer: the mean of a
+    constant is the constant wherever nothing is blocked, a blocked cell zeroes exactly the centres whose polygon covers it (a
+    rectangle of the footprint's size for the unrotated polygon), yaw = 0 makes both layers equal, borders clip the polygon."""
+    rows, cols, res = 96, 80, 0.03   # at 0.03 m checkForSlope can fail (more than 20 of the 29 window cells), at 0.02 m it cannot (29 of 29)
+    g = oracle.Geometry.make(rows, cols, res)
+    fp = oracle.FootprintParams.yaml_defaults()
+    one = np.asfortranarray(np.ones((rows, cols), dtype=np.float32))
+    trav = np.asfortranarray(np.full((rows, cols), 0.75, dtype=np.float32))
+    z = np.asfortranarray(np.zeros((rows, cols), dtype=np.float32))
+    poly = [[0.45, 0.30], [0.45, -0.30], [-0.45, -0.30], [-0.45, 0.30]]       # robot_footprint_parameter.yaml:3
+    tx, trot = oracle.footprint_polygon(g, fp, poly, 0.7854, trav, one, one, z)
+    assert np.all(tx == np.float32(0.75)) and np.all(trot == np.float32(0.75))
+    tx0, trot0 = oracle.footprint_polygon(g, fp, poly, 0.0, trav, one, one, z)
+    assert np.array_equal(tx0, trot0) and np.array_equal(tx0, tx)
+    # blocked cells: slope == 0 in a patch large enough for checkForSlope (its inner cells see 29 zero cells within 3 cells)
+    slope = one.copy(); slope[44:52, 36:44] = 0.0
+    bx, brot = oracle.footprint_polygon(g, fp, poly, 0.7854, trav, slope, one, z)
+    zero_x = np.argwhere(bx == 0.0)
+    assert len(zero_x) > 0 and np.all((bx == 0.0) | (bx == np.float32(0.75)))
+    # unrotated 0.9 m x 0.6 m rectangle: half extents 15 x 10 cells around every blocked cell
+    assert zero_x[:, 0].min() >= 44 - 15 and zero_x[:, 0].max() <= 51 + 15
+    assert zero_x[:, 1].min() >= 36 - 10 and zero_x[:, 1].max() <= 43 + 10
+    assert (brot == 0.0).sum() > 0 and not np.array_equal(bx == 0.0, brot == 0.0)   # the rotated footprint covers other cells

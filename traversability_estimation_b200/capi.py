@@ -18,7 +18,7 @@ KERNEL_AUTO, KERNEL_GENERIC, KERNEL_FUSED = 0, 1, 2
 
 EXPORTS = ["te_create", "te_destroy", "te_last_error", "te_abi_version", "te_set_stream", "te_synchronize",
            "te_set_kernel", "te_get_stats", "te_enable_timing", "te_get_timing", "te_get_flag_counters", "te_get_escalation_stats", "te_fused_plan", "te_slope", "te_normals", "te_step", "te_roughness", "te_chain",
-           "te_chain_batched", "te_footprint", "te_footprint2", "te_check_footprint_paths", "te_check_footprint_paths2", "te_ipc_export", "te_ipc_open", "te_ipc_close", "te_event_create_ipc", "te_event_open_ipc",
+           "te_chain_batched", "te_footprint", "te_footprint2", "te_footprint_polygon", "te_check_footprint_paths", "te_check_footprint_paths2", "te_ipc_export", "te_ipc_open", "te_ipc_close", "te_event_create_ipc", "te_event_open_ipc",
            "te_event_record", "te_event_destroy", "te_halo_pull", "te_host_alloc", "te_host_free"]
 
 
@@ -269,6 +269,15 @@ class Context:
             self._check(self._L.te_footprint2(self._h, C.byref(g), C.byref(slab) if slab is not None else None, C.byref(fp),
                                               _addr(traversability), _addr(slope), _addr(step), _addr(roughness), _addr(elevation),
                                               _addr(out), _addr(slope_fp), _addr(step_fp), _addr(roughness_fp), memory))
+
+    def footprint_polygon(self, g, fp, polygon_xy, yaw, traversability, slope, step, elevation, out_x, out_rot, memory, slab=None, roughness=None):
+        """TraversabilityMap::traversabilityFootprint(yaw): layers traversability_x / traversability_rot for the footprint polygon."""
+        pts = np.ascontiguousarray(polygon_xy, dtype=np.float64).reshape(-1, 2)
+        self._L.te_footprint_polygon.argtypes = [C.c_void_p, C.POINTER(Geometry), C.c_void_p, C.POINTER(FootprintParams), C.c_int32, C.c_void_p,
+                                                 C.c_double] + [C.c_void_p] * 7 + [C.c_int]
+        self._check(self._L.te_footprint_polygon(self._h, C.byref(g), C.byref(slab) if slab is not None else None, C.byref(fp), len(pts),
+                                                 pts.ctypes.data, float(yaw), _addr(traversability), _addr(slope), _addr(step), _addr(roughness),
+                                                 _addr(elevation), _addr(out_x), _addr(out_rot), memory))
 
     def check_footprint_paths(self, g, footprint_layer, traversability_default, path_begin, poses_xy, robot_slope=None):
         """Host convenience: (is_safe uint8[npaths], traversability float64[npaths]); footprint_layer is a column-major host layer;

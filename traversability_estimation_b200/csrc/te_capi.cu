@@ -810,6 +810,58 @@ int te_footprint2(te_ctx* c, const te_geometry* g, const te_slab* slab, const te
   return TE_OK;
 }
 
+int te_footprint_polygon(te_ctx* c, const te_geometry* g, const te_slab* slab, const te_footprint_params* p, int32_t npts,
+                         const double* pts_xy, double yaw, const float* trav, const float* slope, const float* step, const float* rough,
+                         const float* elev, float* out_x, float* out_rot, int memory) {
+  TE_ENTER(c);
+  if (int rc = check_geometry(g)) return rc;
+  if (!p) return fail(TE_ERR_BAD_ARG, "footprint parameters are null");
+  if (npts < 3 || npts > 16 || !pts_xy) return fail(TE_ERR_BAD_ARG, "footprint polygon needs 3 to 16 vertices");
+  if (!std::isfinite(yaw)) return fail(TE_ERR_BAD_ARG, "footprint yaw is not finite");
+  for (int k = 0; k < 2 * npts; ++k)
+    if (!std::isfinite(pts_xy[k])) return fail(TE_ERR_BAD_ARG, "footprint polygon vertex is not finite");
+  if (!trav) return fail(TE_ERR_MISSING_LAYER, "layer traversability is missing");
+  if (!slope) return fail(TE_ERR_MISSING_LAYER, "layer traversability_slope is missing");
+  if (!step) return fail(TE_ERR_MISSING_LAYER, "layer traversability_step is missing");
+  if (!elev) return fail(TE_ERR_MISSING_LAYER, "layer elevation is missing");
+  if (p->verify_roughness && !rough) return fail(TE_ERR_MISSING_LAYER, "layer traversability_roughness is missing (verify_roughness is set)");
+  if (!out_x || !out_rot) return fail(TE_ERR_BAD_ARG, "output layer is null");
+  const bool use_rough = p->verify_roughness != 0;
+  te_slab s;
+  if (int rc = resolve_slab(g, slab, te::footprint_polygon_halo(g, p, npts, pts_xy), &s)) return rc;
+  if (int rc = ensure_geometry(c, g)) return rc;
+  const size_t in_bytes = sizeof(float) * (size_t)g->rows * (s.halo_left + s.col_count + s.halo_right);
+  const size_t out_bytes = sizeof(float) * (size_t)g->rows * s.col_count;
+  const float* in[5] = {trav, slope, step, elev, use_rough ? rough : nullptr};
+  float* o[2] = {out_x, out_rot};
+  if (memory == TE_MEM_HOST) {
+    const int slot_in[5] = {0, 1, 2, 3, 11};
+    for (int k = 0; k < 5; ++k) {
+      if (!in[k]) continue;
+      TE_CUDA(c->stage[slot_in[k]].reserve(in_bytes));
+      TE_CUDA(cudaMemcpyAsync(c->stage[slot_in[k]].p, in[k], in_bytes, cudaMemcpyHostToDevice, c->stream));
+      in[k] = (const float*)c->stage[slot_in[k]].p;
+    }
+    for (int k = 0; k < 2; ++k) {
+      TE_CUDA(c->stage[4 + k].reserve(out_bytes));
+      o[k] = (float*)c->stage[4 + k].p;
+    }
+  }
+  const te::SlabView v = make_view(c, g, s);
+  int nl = 0;
+  int rc = te::launch_footprint_polygon(c->fp, v, g, p, npts, pts_xy, yaw, in[0], in[1], in[2], in[4], in[3], o[0], o[1], c->sms, c->stream, &nl);
+  if (rc != 0) return fail(rc, "polygon footprint sweep failed: %s", c->fp.why.c_str());
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(TE_ERR_CUDA, "polygon footprint launch failed: %s", cudaGetErrorString(e));
+  c->launches += nl;
+  if (memory == TE_MEM_HOST) {
+    TE_CUDA(cudaMemcpyAsync(out_x, o[0], out_bytes, cudaMemcpyDeviceToHost, c->stream));
+    TE_CUDA(cudaMemcpyAsync(out_rot, o[1], out_bytes, cudaMemcpyDeviceToHost, c->stream));
+    TE_CUDA(cudaStreamSynchronize(c->stream));
+  }
+  return TE_OK;
+}
+
 int te_footprint(te_ctx* c, const te_geometry* g, const te_slab* slab, const te_footprint_params* p, const float* trav,
                  const float* slope, const float* step, const float* elev, float* out, float* slope_fp, float* step_fp, int memory) {
   if (p && p->verify_roughness) return fail(TE_ERR_MISSING_LAYER, "verify_roughness is set: call te_footprint2 with the traversability_roughness layer");

@@ -384,9 +384,191 @@ __global__ void __launch_bounds__(256) k_fp_nearest(FpArgs A, unsigned char* __r
   }
 }
 
-// isTraversable for every cell on prefix sums: the visited set is a lattice disk, so "is anything blocked in it" and "sum / count
-// of the visited cells" are 2L+1 column queries instead of ~pi r^2 visits; only when a blocker exists is the ring that holds the
-// first one walked in SpiralIterator order.
+// One warp per input-buffer column: prefix sums of t' = finite(traversability) ? value : default along the row
+// index (double; exact for float32 terms, so the order of summation does not matter) and packed blocked flags.
+__global__ void __launch_bounds__(256) k_fp_prepare_p(FpArgs A, Layers L, const unsigned char* __restrict__ blocked, double* __restrict__ P,
+                                                    unsigned* __restrict__ bits) {
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int lb = warp; lb < A.in_ncols; lb += nwarps) {
+    const float* tcol = L.trav + (size_t)lb * A.rows;
+    const unsigned char* bcol = blocked + (size_t)lb * A.rows;
+    double* pcol = P + (size_t)lb * (A.rows + 1);
+    unsigned* wcol = bits + (size_t)lb * A.words;
+    double carry = 0.0;
+    if (lane == 0) pcol[0] = 0.0;
+    for (int base = 0; base < A.rows; base += 32) {
+      const int i = base + lane;
+      double v = 0.0;
+      bool b = false;
+      if (i < A.rows) {
+        const float t = __ldg(tcol + i);
+        v = finitef(t) ? (double)t : A.tdefault;
+        b = bcol[i] != 0;
+      }
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const double o = __shfl_up_sync(0xffffffffu, v, d);
+        if (lane >= d) v += o;
+      }
+      if (i < A.rows) pcol[i + 1] = carry + v;
+      const unsigned w = __ballot_sync(0xffffffffu, b);
+      if (lane == 0) wcol[base >> 5] = w;
+      carry += __shfl_sync(0xffffffffu, v, 31);
+    }
+  }
+}
+
+// isTraversable for every cell on prefix sums: the visited set is a lattice disk, so "is anything blocked in it"
+// and "sum / count of the visited cells" are 2L+1 column queries instead of ~pi r^2 visits; only when a blocker
+// exists is the ring that holds the first one walked in SpiralIterator order.
+__global__ void __launch_bounds__(256) k_sweep_fast(FpArgs A, Layers L, const unsigned char* __restrict__ blocked, float* __restrict__ out) {
+  const int W = 2 * A.L + 1;
+  // one block = 256 consecutive rows of ONE output column (blockIdx.y): a warp's centres share their column, so everything that
+  // depends only on the column — which disk columns exist, whether any blocked cell lies near the warp at all — is warp-uniform
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = A.out_col0 + (int)blockIdx.y;
+  {
+    const int lane = threadIdx.x & 31, i0 = i - lane;
+    if (i0 >= A.rows) return;  // whole warp beyond the last row
+    const bool active = i < A.rows;
+    const size_t c = (size_t)blockIdx.y * A.rows + (active ? i : 0);
+    const double cx = A.X[active ? i : 0], cy = A.Y[j];
+    // disk columns that exist in the map and in this slab's buffer
+    const int l_lo = max(-A.L, max(-j, A.in_col0 - j)), l_hi = min(A.L, min(A.cols_total - 1 - j, A.in_col0 + A.in_ncols - 1 - j));
+    // ---- warp-wide early out: is any cell blocked in the box of rows [i0 - L, i0 + 31 + L] x disk columns?  (packed flags,
+    //      a few words per column, shared by the 32 centres)  Mostly not: then no lane has anything to look for.
+    bool warp_any;
+    {
+      const int w0 = max(i0 - A.L, 0) >> 5, w1 = min(i0 + 31 + A.L, A.rows - 1) >> 5, nw = w1 - w0 + 1;
+      const int ne = (l_hi - l_lo + 1) * nw;
+      unsigned acc = 0;
+      for (int e = lane; e < ne; e += 32) {
+        const int l = l_lo + e / nw, w = w0 + e % nw;
+        acc |= __ldg(A.bits + (size_t)(j + l - A.in_col0) * A.words + w);
+      }
+      warp_any = __any_sync(0xffffffffu, acc != 0u);
+    }
+    if (!active) return;
+    // ---- nearest blocked cell of the visited set, as a squared index distance ------------------------
+    int best = 0x7fffffff;
+    if (warp_any) {
+      const unsigned char* nr = A.near + (size_t)(j + l_lo - A.in_col0) * A.rows + i;
+      for (int l = l_lo; l <= l_hi; ++l, nr += A.rows) {
+        const int g = (int)__ldg(nr);              // nearest blocked row offset in this column
+        const int hw = A.halfw_c[l + A.L];
+        if (g <= hw) best = min(best, g * g + l * l);
+      }
+      for (int q = 0; q < A.n_fuzzy; ++q) {
+        const int w = A.fuzzy[q];
+        const int di = (int)(signed char)(w & 0xff), dj = (int)(signed char)((w >> 8) & 0xff);
+        const int a = i + di, b = j + dj, lb = b - A.in_col0;
+        if (a < 0 || b < 0 || a >= A.rows || b >= A.cols_total || lb < 0 || lb >= A.in_ncols) continue;
+        const double dx = A.X[a] - cx, dy = A.Y[b] - cy;
+        if (!(dx * dx + dy * dy <= A.rmax2)) continue;
+        if (blocked[(size_t)lb * A.rows + a]) best = min(best, di * di + dj * dj);
+      }
+    }
+    // ---- sums over the visited cells before the first blocked one --------------------------------------
+    const bool any = best != 0x7fffffff;
+    const int dstar = any ? (int)sqrt((double)best) : A.nrings + 1;  // ring of the first blocked cell
+    // The first blocked cell in visit order lies in ring dstar: its index-space radius is in [dstar, dstar + 1) (exactly dstar with
+    // the integer norm).  Within the inner radius the result is 0 (TraversabilityMap.cpp:694-704) whatever the sums are: most
+    // centres near an obstacle end here, without prefix sums or a ring walk.
+    if (any && (A.rmin == 0.0 || (A.int_norm ? (double)dstar : (double)(dstar + 1)) * A.res <= A.rmin)) {
+      out[c] = 0.0f;
+      return;
+    }
+    const signed char* hwt = any ? (A.inner + (size_t)dstar * W) : A.halfw;
+    double t = 0.0, t_b = 0.0;
+    int n = 0;
+    if (!warp_any && i - A.L >= 0 && i + A.L < A.rows) {
+      // nothing blocked near this warp and no clipping along the rows: 2 loads and 2 additions per disk column, offsets from
+      // the constant bank
+      const double* pc0 = A.P + (size_t)(j - A.in_col0) * ((size_t)A.rows + 1) + i;
+      int l = l_lo + A.L;
+      const int l_end = l_hi + A.L;
+      for (; l + 1 <= l_end; l += 2) {
+        t += pc0[A.off_hi[l]] - pc0[A.off_lo[l]];
+        t_b += pc0[A.off_hi[l + 1]] - pc0[A.off_lo[l + 1]];
+      }
+      if (l <= l_end) t += pc0[A.off_hi[l]] - pc0[A.off_lo[l]];
+      t += t_b;
+      n = (int)A.cntp[l_end + 1] - (int)A.cntp[l_lo + A.L];
+    } else {
+      const double* pc = A.P + (size_t)(j + l_lo - A.in_col0) * (A.rows + 1);
+      const size_t pstride = (size_t)A.rows + 1;
+      if (i - A.L >= 0 && i + A.L < A.rows) {  // no clipping along the rows: two independent accumulators
+        int l = l_lo;
+        for (; l + 1 <= l_hi; l += 2, pc += 2 * pstride) {
+          const int h0 = hwt[l + A.L], h1 = hwt[l + 1 + A.L];
+          if (h0 >= 0) { t += pc[i + h0 + 1] - pc[i - h0]; n += 2 * h0 + 1; }
+          if (h1 >= 0) { t_b += pc[pstride + i + h1 + 1] - pc[pstride + i - h1]; n += 2 * h1 + 1; }
+        }
+        if (l <= l_hi) {
+          const int h0 = hwt[l + A.L];
+          if (h0 >= 0) { t += pc[i + h0 + 1] - pc[i - h0]; n += 2 * h0 + 1; }
+        }
+      } else {
+        for (int l = l_lo; l <= l_hi; ++l, pc += pstride) {
+          const int hw = hwt[l + A.L];
+          if (hw < 0) continue;
+          const int a0 = max(i - hw, 0), a1 = min(i + hw, A.rows - 1);
+          t += pc[a1 + 1] - pc[a0];
+          n += a1 - a0 + 1;
+        }
+      }
+      t += t_b;
+    }
+    float result;
+    if (!any) {
+      for (int q = 0; q < A.n_fuzzy; ++q) {  // on-circle cells belong to the last ring: they are visited last
+        const int w = A.fuzzy[q];
+        const int di = (int)(signed char)(w & 0xff), dj = (int)(signed char)((w >> 8) & 0xff);
+        const int a = i + di, b = j + dj, lb = b - A.in_col0;
+        if (a < 0 || b < 0 || a >= A.rows || b >= A.cols_total || lb < 0 || lb >= A.in_ncols) continue;
+        const double dx = A.X[a] - cx, dy = A.Y[b] - cy;
+        if (!(dx * dx + dy * dy <= A.rmax2)) continue;
+        const float v = __ldg(L.trav + (size_t)lb * A.rows + a);
+        t += finitef(v) ? (double)v : A.tdefault;
+        ++n;
+      }
+      t /= (double)n;
+      result = (float)t;
+    } else {
+      // walk ring dstar in visit order up to its first blocked cell
+      int di = 0, dj = 0;
+      for (int k = A.ring_start[dstar]; k < A.ring_start[dstar + 1]; ++k) {
+        const int w = __ldg(A.spiral + k);
+        di = (int)(signed char)(w & 0xff);
+        dj = (int)(signed char)((w >> 8) & 0xff);
+        const int a = i + di, b = j + dj, lb = b - A.in_col0;
+        if (a < 0 || b < 0 || a >= A.rows || b >= A.cols_total || lb < 0 || lb >= A.in_ncols) continue;
+        if (w & 0x10000) {
+          const double dx = A.X[a] - cx, dy = A.Y[b] - cy;
+          if (!(dx * dx + dy * dy <= A.rmax2)) continue;
+        }
+        const size_t cc = (size_t)lb * A.rows + a;
+        if (blocked[cc]) break;
+        const float v = __ldg(L.trav + cc);
+        t += finitef(v) ? (double)v : A.tdefault;
+        ++n;
+      }
+      const int d2 = di * di + dj * dj;
+      const double nr = A.int_norm ? (double)(int)sqrt((double)d2) : sqrt((double)d2);
+      const double uR = nr * A.res;
+      if (A.rmin == 0.0 || uR <= A.rmin) {
+        result = 0.0f;
+      } else {
+        const double factor = ((uR - A.rmin) / (A.rmax - A.rmin) + 1.0) / 2.0;
+        t *= factor / (double)n;
+        result = (float)t;
+      }
+    }
+    out[c] = result;
+  }
+}
+
 // The sweep, tiled: a CTA owns TR x TC centres and stages what their disks touch — the column prefix sums of t' over the tile's
 // rows plus L rows of halo, for the tile's columns plus L columns of halo — in shared memory, computing them in place from the
 // traversability layer (prefix sums local to the tile: small magnitudes, no 8-byte-per-cell array in HBM).  k_sweep_fast sends
@@ -603,6 +785,174 @@ __global__ void __launch_bounds__(256) k_sweep_tile(FpArgs A, Layers L, const un
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------------
+// Polygonal footprint sweep: TraversabilityMap::traversabilityFootprint(double footprintYaw), TraversabilityMap.cpp:239-305, with the
+// polygon isTraversable (:592-645).  Every cell gets the footprint polygon placed at its centre; the value is 0 when a cell of the
+// polygon fails isTraversableForFilters, otherwise the mean of t' over the polygon's cells (traversabilityDefault_ when it covers
+// none).  The set of cells inside the polygon is the same offset pattern for every centre EXCEPT for offsets whose cell centre lies
+// on (within rounding of) an edge: grid_map::Polygon::isInside decides those on absolute double coordinates, differently from
+// centre to centre.  The host classifies the offsets once (launch_footprint_polygon): certain-in cells become per-column runs that
+// are summed from the tile's prefix sums; the few uncertain offsets are decided per centre with the reference's own arithmetic —
+// cooperatively when the decision does not depend on the centre's row (an edge parallel to the x axis through cell centres: the
+// YAML footprint at 0.02 m has 92 such offsets), 32 offsets per warp pass.
+constexpr int PTR = 64, PTC = 16;  // tile of centres: rows x columns
+constexpr int PMAXV = 16;          // polygon vertices
+constexpr int PB = 130;            // pitch of a staged blocked-count column (uint16)
+struct PolyArgs {
+  int Lp;             // reach of the polygon in cells (<= 31)
+  int nruns, nfz, npts;
+  const int* runs;    // (dj & 0xff) | (lo & 0xff) << 8 | (hi & 0xff) << 16: rows i+lo .. i+hi of column j+dj are certainly inside
+  const int* fz;      // (di & 0xff) | (dj & 0xff) << 8 | flags << 16: uncertain offsets; flag bit 0: depends on the centre's row
+  double r00, r01, r10, r11;  // Eigen::Quaternion::toRotationMatrix of (cos(yaw/2), 0, 0, sin(yaw/2)), upper-left 2 x 2
+  double px[PMAXV], py[PMAXV];
+};
+
+// grid_map::Polygon::isInside for the polygon placed at (cx, cy): vertices = R * p + centre in the operand order of Eigen's
+// Transform * vector (oracle: teo_footprint_polygon), crossing-number test over (v[i], v[i-1]).
+__device__ bool poly_inside_d(const PolyArgs& Q, double cx, double cy, double ptx, double pty) {
+  int cross = 0;
+  const int last = Q.npts - 1;
+  double jx = cx + ((Q.r00 * Q.px[last] + Q.r01 * Q.py[last]) + 0.0);
+  double jy = cy + ((Q.r10 * Q.px[last] + Q.r11 * Q.py[last]) + 0.0);
+  for (int k = 0; k < Q.npts; ++k) {
+    const double ix = cx + ((Q.r00 * Q.px[k] + Q.r01 * Q.py[k]) + 0.0);
+    const double iy = cy + ((Q.r10 * Q.px[k] + Q.r11 * Q.py[k]) + 0.0);
+    if (((iy > pty) != (jy > pty)) && (ptx < (jx - ix) * (pty - iy) / (jy - iy) + ix)) ++cross;
+    jx = ix;
+    jy = iy;
+  }
+  return (cross & 1) != 0;
+}
+
+__global__ void __launch_bounds__(256) k_poly_tile(FpArgs A, PolyArgs Q, const float* __restrict__ trav, const unsigned char* __restrict__ blocked,
+                                                   float* __restrict__ out) {
+  extern __shared__ double sP[];  // [NC][PS] prefix sums of t'; then [NC][PB] uint16 prefix counts of blocked; then [NC][128] blocked bytes
+  const int Lr = Q.Lp, NR = PTR + 2 * Lr, NC = PTC + 2 * Lr, PS = NR + 1;
+  unsigned short* sB = reinterpret_cast<unsigned short*>(sP + (size_t)NC * PS);
+  unsigned char* sBlk = reinterpret_cast<unsigned char*>(sB + (size_t)NC * PB);
+  const int r0 = (int)blockIdx.x * PTR, c0 = A.out_col0 + (int)blockIdx.y * PTC;
+  const int rb = r0 - Lr, cb = c0 - Lr;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // ---- phase 1 (as in k_sweep_tile, plus the blocked counts): one warp per staged column, four rows per lane
+  int anyb = 0;
+  for (int cc = warp; cc < NC; cc += 8) {
+    const int gcol = cb + cc, lb = gcol - A.in_col0;
+    const bool col_ok = gcol >= 0 && gcol < A.cols_total && lb >= 0 && lb < A.in_ncols;
+    const float* tcol = trav + (size_t)(col_ok ? lb : 0) * A.rows;
+    const unsigned char* bcol = blocked + (size_t)(col_ok ? lb : 0) * A.rows;
+    double v[4];
+    int cb4[4];
+    unsigned bw = 0;
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+      const int k = 4 * lane + m, row = rb + k;
+      v[m] = 0.0;
+      cb4[m] = 0;
+      if (k < NR && col_ok && row >= 0 && row < A.rows) {
+        const float t = __ldg(tcol + row);
+        v[m] = finitef(t) ? (double)t : A.tdefault;
+        cb4[m] = bcol[row] != 0 ? 1 : 0;
+        bw |= (unsigned)cb4[m] << (8 * m);
+      }
+    }
+    anyb |= (int)bw;
+    reinterpret_cast<unsigned*>(sBlk)[cc * 32 + lane] = bw;
+    v[1] += v[0]; v[2] += v[1]; v[3] += v[2];
+    cb4[1] += cb4[0]; cb4[2] += cb4[1]; cb4[3] += cb4[2];
+    double tot = v[3];
+    int ctot = cb4[3];
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const double o = __shfl_up_sync(0xffffffffu, tot, d);
+      const int oc = __shfl_up_sync(0xffffffffu, ctot, d);
+      if (lane >= d) { tot += o; ctot += oc; }
+    }
+    double before = __shfl_up_sync(0xffffffffu, tot, 1);
+    int cbefore = __shfl_up_sync(0xffffffffu, ctot, 1);
+    if (lane == 0) { before = 0.0; cbefore = 0; }
+    double* pcol = sP + (size_t)cc * PS;
+    unsigned short* ccol = sB + (size_t)cc * PB;
+    if (lane == 0) { pcol[0] = 0.0; ccol[0] = 0; }
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+      const int k = 4 * lane + m;
+      if (k < NR) { pcol[k + 1] = before + v[m]; ccol[k + 1] = (unsigned short)(cbefore + cb4[m]); }
+    }
+  }
+  const bool tile_any = __syncthreads_or(anyb) != 0;
+  // ---- phase 2: a warp is 32 consecutive rows of one column at a time (4 columns per warp)
+  const int i = r0 + (warp & 1) * 32 + lane;
+  const int i0 = i - lane;
+  if (i0 >= A.rows) return;
+  const bool active = i < A.rows;
+  const int ic = active ? i : A.rows - 1;
+  const double cx = A.X[ic];
+  const int k0 = ic - rb;
+  for (int q = 0; q < PTC / 4; ++q) {
+    const int j = c0 + (warp >> 1) * (PTC / 4) + q;
+    if (j >= A.out_col0 + A.out_ncols) break;
+    const double cy = A.Y[j];
+    double t = 0.0;
+    int n = 0, nblk = 0;
+    // certain cells: per-column runs from the prefix sums (cells outside the map were staged as t' = 0, not blocked)
+    for (int r = 0; r < Q.nruns; ++r) {
+      const int w = __ldg(Q.runs + r);
+      const int dj = (int)(signed char)(w & 0xff), lo = (int)(signed char)((w >> 8) & 0xff), hi = (int)(signed char)((w >> 16) & 0xff);
+      const int b = j + dj, lb = b - A.in_col0;
+      if (b < 0 || b >= A.cols_total || lb < 0 || lb >= A.in_ncols) continue;
+      const int a0 = max(ic + lo, 0), a1 = min(ic + hi, A.rows - 1);
+      if (a0 > a1) continue;
+      const int cc = b - cb;
+      const double* pc = sP + (size_t)cc * PS + k0;
+      t += pc[hi + 1] - pc[lo];
+      n += a1 - a0 + 1;
+      if (tile_any) {
+        const unsigned short* bc = sB + (size_t)cc * PB + k0;
+        nblk += (int)bc[hi + 1] - (int)bc[lo];
+      }
+    }
+    // uncertain offsets, 32 per pass: lane l decides offset base + l when the decision is the same for every row of the column
+    for (int base = 0; base < Q.nfz; base += 32) {
+      const int idx = base + lane;
+      int w = 0;
+      bool cand = false;
+      if (idx < Q.nfz) {
+        w = __ldg(Q.fz + idx);
+        const int di = (int)(signed char)(w & 0xff), dj = (int)(signed char)((w >> 8) & 0xff);
+        if ((w >> 16) & 1) {
+          cand = true;  // depends on the row: every lane decides for itself below
+        } else {
+          const int a = ic + di, b = j + dj;
+          // the decision does not depend on the row, so any row's coordinates will do — but they must exist
+          const int ar = min(max(a, 0), A.rows - 1), icr = ar - di;
+          if (b >= 0 && b < A.cols_total && icr >= 0 && icr < A.rows) cand = poly_inside_d(Q, A.X[icr], cy, A.X[ar], A.Y[b]);
+        }
+      }
+      unsigned m = __ballot_sync(0xffffffffu, cand);
+      while (m) {
+        const int src = __ffs((int)m) - 1;
+        m &= m - 1;
+        const int wv = __shfl_sync(0xffffffffu, w, src);
+        const int di = (int)(signed char)(wv & 0xff), dj = (int)(signed char)((wv >> 8) & 0xff);
+        const int a = ic + di, b = j + dj, lb = b - A.in_col0;
+        if (a < 0 || b < 0 || a >= A.rows || b >= A.cols_total || lb < 0 || lb >= A.in_ncols) continue;
+        if (((wv >> 16) & 1) && !poly_inside_d(Q, cx, cy, A.X[a], A.Y[b])) continue;
+        const int cc = b - cb, kk = a - rb;
+        if (sBlk[cc * 128 + kk]) { ++nblk; continue; }
+        const double* pc = sP + (size_t)cc * PS + kk;
+        t += pc[1] - pc[0];
+        ++n;
+      }
+    }
+    if (!active) continue;
+    float result;
+    if (nblk > 0) result = 0.0f;                       // :297 / :301
+    else if (n == 0) result = (float)A.tdefault;       // :625-628
+    else result = (float)(t / (double)n);              // :630
+    out[(size_t)(j - A.out_col0) * A.rows + i] = result;
+  }
+}
+
 // TraversabilityMap::checkCircularFootprintPath (TraversabilityMap.cpp:345-462) for a batch of paths — one thread per path — on a
 // traversability_footprint layer that is valid everywhere: every isTraversable(center, ...) takes the memoised branch
 // (:667-673), centres outside the map the default branch (:660-666).  No inclination check, no polygons.
@@ -730,6 +1080,11 @@ void FootprintState::release() {
   if (d_tables) cudaFree(d_tables);
   if (d_prefix) cudaFree(d_prefix);
   if (d_list) cudaFree(d_list);
+  for (int k = 0; k < 2; ++k) {
+    if (d_poly[k]) cudaFree(d_poly[k]);
+    d_poly[k] = nullptr;
+    poly_cap[k] = 0;
+  }
   d_spiral = d_block = d_tables = d_prefix = d_list = nullptr;
   spiral_cap = block_cap = tables_cap = prefix_cap = list_cap = 0;
   tables_valid = false;
@@ -753,6 +1108,53 @@ int footprint_halo(const te_geometry* g, const te_footprint_params* p) {
   // predicates of a visited cell: slope window 3 cells; step: 2.5-cell circle + 3x3 submap + gap walk
   const int walk = (int)std::ceil(p->max_gap_width / res) + 1;
   return spiral + std::max(4, 3 + 1 + walk);
+}
+
+// isTraversableForFilters for every cell of the slab + halo into st.d_block (k_pred_classify + k_pred_heavy); fills the geometry /
+// parameter part of the kernel arguments.  Shared by the circular and the polygonal sweep.
+int run_predicates(FootprintState& st, const SlabView& v, const te_geometry* g, const te_footprint_params* p, const float* trav,
+                   const float* slope, const float* step, const float* rough, const float* elev, float* slope_fp, float* step_fp,
+                   float* rough_fp, int sms, cudaStream_t s, FpArgs* out_args) {
+  const double rmax = p->radius + p->offset;
+  const size_t ncell_in = (size_t)v.rows * v.in_ncols;
+  if (st.block_cap < ncell_in) {
+    if (st.d_block) cudaFree(st.d_block);
+    st.d_block = nullptr;
+    st.block_cap = 0;
+    if (cudaMalloc(&st.d_block, ncell_in) != cudaSuccess) { st.why = "cudaMalloc(predicate bytes) failed"; return TE_ERR_CUDA; }
+    st.block_cap = ncell_in;
+  }
+  FpArgs a{};
+  a.rows = v.rows; a.cols_total = v.cols_total; a.in_col0 = v.in_col0; a.in_ncols = v.in_ncols;
+  a.out_col0 = v.out_col0; a.out_ncols = v.out_ncols;
+  a.res = g->resolution; a.lenx = g->length_x; a.leny = g->length_y; a.posx = g->position_x; a.posy = g->position_y;
+  a.X = v.X; a.Y = v.Y;
+  a.rmin = p->radius; a.rmax = rmax; a.rmax2 = rmax * rmax; a.tdefault = p->traversability_default;
+  a.maxgap = p->max_gap_width; a.crit = p->critical_step_height; a.int_norm = p->radius_is_integer_norm;
+  a.verify_rough = (p->verify_roughness != 0 && rough != nullptr) ? 1 : 0;
+  a.n_spiral = st.n_spiral; a.spiral = (const int*)st.d_spiral;
+  a.slope_R = (int)std::floor(3.0 * g->resolution / g->resolution) + 1;
+  a.step_R = (int)std::floor(2.5 * g->resolution / g->resolution) + 1;
+  const Layers L{trav, slope, step, elev, rough};
+  const long long t1 = (long long)ncell_in;
+  const int g1 = (int)std::min<long long>((t1 + 127) / 128, (long long)sms * 16);
+  {
+    if (ncell_in >= ((size_t)1 << 32)) { st.why = "slab of 2^32 or more cells"; return TE_ERR_UNSUPPORTED; }
+    if (st.list_cap < ncell_in + 1) {
+      if (st.d_list) cudaFree(st.d_list);
+      st.d_list = nullptr; st.list_cap = 0;
+      if (cudaMalloc(&st.d_list, sizeof(unsigned) * (ncell_in + 1)) != cudaSuccess) { st.why = "cudaMalloc(predicate work list) failed"; return TE_ERR_CUDA; }
+      st.list_cap = ncell_in + 1;
+    }
+    unsigned* cnt = (unsigned*)st.d_list;          // word 0: list length; entries follow
+    unsigned* lst = cnt + 1;
+    cudaMemsetAsync(cnt, 0, sizeof(unsigned), s);
+    const dim3 gc((unsigned)((v.rows + 255) / 256), (unsigned)v.in_ncols);
+    k_pred_classify<<<gc, 256, 0, s>>>(a, L, (unsigned char*)st.d_block, slope_fp, step_fp, rough_fp, lst, cnt);
+    k_pred_heavy<<<std::max(g1, 1), 128, 0, s>>>(a, L, (unsigned char*)st.d_block, slope_fp, step_fp, rough_fp, lst, cnt);
+  }
+  *out_args = a;
+  return 0;
 }
 
 int launch_footprint(FootprintState& st, const SlabView& v, const te_geometry* g, const te_footprint_params* p,
@@ -779,44 +1181,12 @@ int launch_footprint(FootprintState& st, const SlabView& v, const te_geometry* g
     st.valid = true;
     st.tables_valid = false;
   }
-  const size_t ncell_in = (size_t)v.rows * v.in_ncols;
-  if (st.block_cap < ncell_in) {
-    if (st.d_block) cudaFree(st.d_block);
-    st.d_block = nullptr;
-    st.block_cap = 0;
-    if (cudaMalloc(&st.d_block, ncell_in) != cudaSuccess) { st.why = "cudaMalloc(predicate bytes) failed"; return TE_ERR_CUDA; }
-    st.block_cap = ncell_in;
-  }
   FpArgs a{};
-  a.rows = v.rows; a.cols_total = v.cols_total; a.in_col0 = v.in_col0; a.in_ncols = v.in_ncols;
-  a.out_col0 = v.out_col0; a.out_ncols = v.out_ncols;
-  a.res = g->resolution; a.lenx = g->length_x; a.leny = g->length_y; a.posx = g->position_x; a.posy = g->position_y;
-  a.X = v.X; a.Y = v.Y;
-  a.rmin = p->radius; a.rmax = rmax; a.rmax2 = rmax * rmax; a.tdefault = p->traversability_default;
-  a.maxgap = p->max_gap_width; a.crit = p->critical_step_height; a.int_norm = p->radius_is_integer_norm;
-  a.verify_rough = (p->verify_roughness != 0 && rough != nullptr) ? 1 : 0;
-  a.n_spiral = st.n_spiral; a.spiral = (const int*)st.d_spiral;
-  a.slope_R = (int)std::floor(3.0 * g->resolution / g->resolution) + 1;
-  a.step_R = (int)std::floor(2.5 * g->resolution / g->resolution) + 1;
+  if (int rc = run_predicates(st, v, g, p, trav, slope, step, rough, elev, slope_fp, step_fp, rough_fp, sms, s, &a)) return rc;
+  const size_t ncell_in = (size_t)v.rows * v.in_ncols;
   const Layers L{trav, slope, step, elev, rough};
   const long long t1 = (long long)ncell_in, t2 = (long long)v.rows * v.out_ncols;
-  const int g1 = (int)std::min<long long>((t1 + 127) / 128, (long long)sms * 16);
   const int g2 = (int)std::min<long long>((t2 + 255) / 256, (long long)sms * 8);
-  {
-    if (ncell_in >= ((size_t)1 << 32)) { st.why = "slab of 2^32 or more cells"; return TE_ERR_UNSUPPORTED; }
-    if (st.list_cap < ncell_in + 1) {
-      if (st.d_list) cudaFree(st.d_list);
-      st.d_list = nullptr; st.list_cap = 0;
-      if (cudaMalloc(&st.d_list, sizeof(unsigned) * (ncell_in + 1)) != cudaSuccess) { st.why = "cudaMalloc(predicate work list) failed"; return TE_ERR_CUDA; }
-      st.list_cap = ncell_in + 1;
-    }
-    unsigned* cnt = (unsigned*)st.d_list;          // word 0: list length; entries follow
-    unsigned* lst = cnt + 1;
-    cudaMemsetAsync(cnt, 0, sizeof(unsigned), s);
-    const dim3 gc((unsigned)((v.rows + 255) / 256), (unsigned)v.in_ncols);
-    k_pred_classify<<<gc, 256, 0, s>>>(a, L, (unsigned char*)st.d_block, slope_fp, step_fp, rough_fp, lst, cnt);
-    k_pred_heavy<<<std::max(g1, 1), 128, 0, s>>>(a, L, (unsigned char*)st.d_block, slope_fp, step_fp, rough_fp, lst, cnt);
-  }
   const int Lmax = (int)std::floor(rmax / g->resolution + 1e-9);
   const bool fast = Lmax <= 31 && v.out_ncols <= 65535 && std::getenv("TE_FOOTPRINT_BRUTE") == nullptr;
   if (!fast) {
@@ -885,24 +1255,31 @@ int launch_footprint(FootprintState& st, const SlabView& v, const te_geometry* g
     st.tables_valid = true;
   }
   const int words = (v.rows + 31) / 32;
+#ifdef TE_CALIBRATION  // calibration builds only: the tiled variant for A/B timing (tools/gpu_r2_*.sh)
+  const bool tiled = std::getenv("TE_FOOTPRINT_TILE") != nullptr;
+#else
+  const bool tiled = false;
+#endif
+  // global prefix sums (k_sweep_fast) or none (k_sweep_tile builds them per tile in shared memory)
+  const size_t pbytes = tiled ? 0 : sizeof(double) * (size_t)(v.rows + 1) * v.in_ncols;
   const size_t wbytes = (sizeof(unsigned) * (size_t)words * v.in_ncols + 15) / 16 * 16;
   const size_t gbytes = ncell_in;
-  if (st.prefix_cap < wbytes + gbytes) {
+  if (st.prefix_cap < pbytes + wbytes + gbytes) {
     if (st.d_prefix) cudaFree(st.d_prefix);
     st.d_prefix = nullptr; st.prefix_cap = 0;
-    if (cudaMalloc(&st.d_prefix, wbytes + gbytes) != cudaSuccess) { st.why = "cudaMalloc(footprint flag words) failed"; return TE_ERR_CUDA; }
-    st.prefix_cap = wbytes + gbytes;
+    if (cudaMalloc(&st.d_prefix, pbytes + wbytes + gbytes) != cudaSuccess) { st.why = "cudaMalloc(footprint prefix sums) failed"; return TE_ERR_CUDA; }
+    st.prefix_cap = pbytes + wbytes + gbytes;
   }
   a.L = st.L; a.nrings = st.nrings; a.n_fuzzy = st.n_fuzzy; a.words = words;
   a.ring_start = (const int*)((char*)st.d_tables + st.off_ring);
   a.fuzzy = (const int*)((char*)st.d_tables + st.off_fuzzy);
   a.halfw = (const signed char*)((char*)st.d_tables + st.off_halfw);
   a.inner = (const signed char*)((char*)st.d_tables + st.off_inner);
-  a.P = nullptr;
-  a.bits = (const unsigned*)st.d_prefix;
-  a.near = (const unsigned char*)st.d_prefix + wbytes;
+  a.P = tiled ? nullptr : (const double*)st.d_prefix;
+  a.bits = (const unsigned*)((char*)st.d_prefix + pbytes);
+  a.near = (const unsigned char*)st.d_prefix + pbytes + wbytes;
   std::memcpy(a.halfw_c, st.h_halfw, sizeof(a.halfw_c));
-  const int pstride = TR + 2 * st.L + 1;  // pitch of a staged prefix-sum column in k_sweep_tile
+  const int pstride = tiled ? TR + 2 * st.L + 1 : v.rows + 1;  // pitch of a prefix-sum column
   {
     a.cntp[0] = 0;
     for (int k = 0; k < 64; ++k) {
@@ -914,17 +1291,136 @@ int launch_footprint(FootprintState& st, const SlabView& v, const te_geometry* g
   }
   const int g3 = std::min(sms * 8, (v.in_ncols + 7) / 8);
   const int g1b = (int)std::min<long long>((t1 + 255) / 256, (long long)sms * 8);
-  k_fp_prepare<<<std::max(g3, 1), 256, 0, s>>>(a, (const unsigned char*)st.d_block, (unsigned*)st.d_prefix);
-  k_fp_nearest<<<std::max(g1b, 1), 256, 0, s>>>(a, (unsigned char*)st.d_prefix + wbytes);
-  const size_t smem = sizeof(double) * (size_t)(TC + 2 * st.L) * pstride + (size_t)(TC + 2 * st.L) * (TR + 128);
-  if (!st.tile_attr) {
-    if (cudaFuncSetAttribute(k_sweep_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * (TC + 62) * (TR + 63) + (TC + 62) * (TR + 128))) != cudaSuccess) {
+  if (tiled) k_fp_prepare<<<std::max(g3, 1), 256, 0, s>>>(a, (const unsigned char*)st.d_block, (unsigned*)((char*)st.d_prefix + pbytes));
+  else k_fp_prepare_p<<<std::max(g3, 1), 256, 0, s>>>(a, L, (const unsigned char*)st.d_block, (double*)st.d_prefix, (unsigned*)((char*)st.d_prefix + pbytes));
+  k_fp_nearest<<<std::max(g1b, 1), 256, 0, s>>>(a, (unsigned char*)st.d_prefix + pbytes + wbytes);
+  if (tiled) {
+    const size_t smem = sizeof(double) * (size_t)(TC + 2 * st.L) * pstride + (size_t)(TC + 2 * st.L) * (TR + 128);
+    if (!st.tile_attr) {
+      if (cudaFuncSetAttribute(k_sweep_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * (TC + 62) * (TR + 63) + (TC + 62) * (TR + 128))) != cudaSuccess) {
+        st.why = "cudaFuncSetAttribute(max dynamic shared memory) failed"; return TE_ERR_CUDA;
+      }
+      st.tile_attr = true;
+    }
+    k_sweep_tile<<<dim3((unsigned)((v.rows + TR - 1) / TR), (unsigned)((v.out_ncols + TC - 1) / TC)), 256, smem, s>>>(a, L, (const unsigned char*)st.d_block, out);
+  } else {
+    k_sweep_fast<<<dim3((unsigned)((v.rows + 255) / 256), (unsigned)v.out_ncols), 256, 0, s>>>(a, L, (const unsigned char*)st.d_block, out);
+  }
+  if (launches) *launches = 5;
+  return 0;
+}
+
+int polygon_reach(const te_geometry* g, int npts, const double* pts_xy) {
+  double r = 0.0;
+  for (int k = 0; k < npts; ++k) r = std::max(r, std::hypot(pts_xy[2 * k], pts_xy[2 * k + 1]));
+  return (int)std::ceil(r / g->resolution) + 1;
+}
+
+int footprint_polygon_halo(const te_geometry* g, const te_footprint_params* p, int npts, const double* pts_xy) {
+  const int walk = (int)std::ceil(p->max_gap_width / g->resolution) + 1;
+  return polygon_reach(g, npts, pts_xy) + std::max(4, 3 + 1 + walk);
+}
+
+namespace {
+// Offsets (di, dj) of the cells inside the polygon placed at a cell centre, relative to that centre: certain-in cells as runs per
+// column offset, cells within `tol` of a comparison of grid_map::Polygon::isInside as the uncertain list.
+struct PolyTables {
+  std::vector<int> runs, fz;
+};
+bool classify_polygon(double res, int Lp, int npts, const double* px, const double* py, const double R[4], PolyTables* out, std::string* why) {
+  std::vector<double> vx(npts), vy(npts);
+  for (int k = 0; k < npts; ++k) {
+    vx[k] = (R[0] * px[k] + R[1] * py[k]) + 0.0;
+    vy[k] = (R[2] * px[k] + R[3] * py[k]) + 0.0;
+  }
+  const double tol = 1e-7 * res;  // rounding moves a comparison by ~1e-13 m at most; anything closer than this is decided per centre
+  out->runs.clear();
+  out->fz.clear();
+  for (int dj = -Lp; dj <= Lp; ++dj) {
+    int run_lo = 0;
+    bool in_run = false;
+    for (int di = -Lp; di <= Lp + 1; ++di) {
+      bool inside = false, fuzzy = false, row_dep = false;
+      if (di <= Lp) {
+        // cell centre relative to the polygon's centre: X decreases with the row index, Y with the column index
+        const double ptx = -res * (double)di, pty = -res * (double)dj;
+        int cross = 0;
+        for (int i = 0, j = npts - 1; i < npts; j = i++) {
+          // equal y (bitwise; per centre both get the same centre coordinate added): (v[i].y > pt.y) == (v[j].y > pt.y) always
+          if (vy[i] == vy[j]) continue;
+          const bool ui = std::fabs(vy[i] - pty) < tol, uj = std::fabs(vy[j] - pty) < tol;
+          if (ui || uj) fuzzy = true;  // (v.y > pt.y) may fall either way: depends on the column pair only
+          const bool ci = vy[i] > pty, cj = vy[j] > pty;
+          if ((ci != cj) || ui || uj) {
+            const double thr = (vx[j] - vx[i]) * (pty - vy[i]) / (vy[j] - vy[i]) + vx[i];
+            // the x comparison involves the centre's row; so does a threshold that is a quotient of two rounding-sized numbers
+            if (std::fabs(ptx - thr) < tol || std::fabs(vy[j] - vy[i]) < 1e3 * tol) { fuzzy = true; row_dep = true; }
+            if ((ci != cj) && ptx < thr) ++cross;
+          }
+        }
+        inside = (cross & 1) != 0;
+      }
+      if (fuzzy) {
+        if (out->fz.size() >= 4096) { *why = "footprint polygon has more than 4096 cells on its outline"; return false; }
+        out->fz.push_back((di & 0xff) | ((dj & 0xff) << 8) | ((row_dep ? 1 : 0) << 16));
+        inside = false;
+      }
+      if (inside && !in_run) { in_run = true; run_lo = di; }
+      if (!inside && in_run) {
+        in_run = false;
+        out->runs.push_back((dj & 0xff) | ((run_lo & 0xff) << 8) | (((di - 1) & 0xff) << 16));
+      }
+    }
+  }
+  return true;
+}
+}  // namespace
+
+// traversabilityFootprint(yaw): predicates once, then one tiled launch per polygon (unrotated -> out_x, rotated -> out_rot).
+int launch_footprint_polygon(FootprintState& st, const SlabView& v, const te_geometry* g, const te_footprint_params* p, int npts,
+                             const double* pts_xy, double yaw, const float* trav, const float* slope, const float* step,
+                             const float* rough, const float* elev, float* out_x, float* out_rot, int sms, cudaStream_t s, int* launches) {
+  if (npts < 3 || npts > PMAXV) { st.why = "footprint polygon needs 3 to 16 vertices"; return TE_ERR_UNSUPPORTED; }
+  const int Lp = polygon_reach(g, npts, pts_xy);
+  if (Lp > 31) { st.why = "footprint polygon reaches further than 31 cells from its centre"; return TE_ERR_UNSUPPORTED; }
+  FpArgs a{};
+  if (int rc = run_predicates(st, v, g, p, trav, slope, step, rough, elev, nullptr, nullptr, nullptr, sms, s, &a)) return rc;
+  const size_t smem = sizeof(double) * (size_t)(PTC + 2 * Lp) * (PTR + 2 * Lp + 1) + (size_t)(PTC + 2 * Lp) * (PB * 2 + 128);
+  if (!st.poly_attr) {
+    const size_t smax = sizeof(double) * (size_t)(PTC + 62) * (PTR + 63) + (size_t)(PTC + 62) * (PB * 2 + 128);
+    if (cudaFuncSetAttribute(k_poly_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smax) != cudaSuccess) {
       st.why = "cudaFuncSetAttribute(max dynamic shared memory) failed"; return TE_ERR_CUDA;
     }
-    st.tile_attr = true;
+    st.poly_attr = true;
   }
-  k_sweep_tile<<<dim3((unsigned)((v.rows + TR - 1) / TR), (unsigned)((v.out_ncols + TC - 1) / TC)), 256, smem, s>>>(a, L, (const unsigned char*)st.d_block, out);
-  if (launches) *launches = 5;
+  int nl = 2;
+  for (int which = 0; which < 2; ++which) {
+    PolyArgs q{};
+    q.Lp = Lp; q.npts = npts;
+    const double w = which ? std::cos(0.5 * yaw) : 1.0, z = which ? std::sin(0.5 * yaw) : 0.0;
+    const double tz = 2.0 * z, twz = tz * w, tzz = tz * z;
+    q.r00 = 1.0 - (0.0 + tzz); q.r01 = 0.0 - twz; q.r10 = 0.0 + twz; q.r11 = 1.0 - (0.0 + tzz);
+    for (int k = 0; k < npts; ++k) { q.px[k] = pts_xy[2 * k]; q.py[k] = pts_xy[2 * k + 1]; }
+    const double R[4] = {q.r00, q.r01, q.r10, q.r11};
+    PolyTables tb;
+    if (!classify_polygon(g->resolution, Lp, npts, q.px, q.py, R, &tb, &st.why)) return TE_ERR_UNSUPPORTED;
+    const size_t bytes = sizeof(int) * (tb.runs.size() + tb.fz.size() + 2);
+    void*& d = st.d_poly[which];
+    if (st.poly_cap[which] < bytes) {
+      if (d) { cudaStreamSynchronize(s); cudaFree(d); }
+      d = nullptr; st.poly_cap[which] = 0;
+      if (cudaMalloc(&d, bytes) != cudaSuccess) { st.why = "cudaMalloc(polygon tables) failed"; return TE_ERR_CUDA; }
+      st.poly_cap[which] = bytes;
+    }
+    int* dr = (int*)d;
+    int* df = dr + tb.runs.size() + 1;
+    if (!tb.runs.empty() && cudaMemcpyAsync(dr, tb.runs.data(), sizeof(int) * tb.runs.size(), cudaMemcpyHostToDevice, s) != cudaSuccess) { st.why = "polygon table upload failed"; return TE_ERR_CUDA; }
+    if (!tb.fz.empty() && cudaMemcpyAsync(df, tb.fz.data(), sizeof(int) * tb.fz.size(), cudaMemcpyHostToDevice, s) != cudaSuccess) { st.why = "polygon table upload failed"; return TE_ERR_CUDA; }
+    q.runs = dr; q.fz = df; q.nruns = (int)tb.runs.size(); q.nfz = (int)tb.fz.size();
+    k_poly_tile<<<dim3((unsigned)((v.rows + PTR - 1) / PTR), (unsigned)((v.out_ncols + PTC - 1) / PTC)), 256, smem, s>>>(
+        a, q, trav, (const unsigned char*)st.d_block, which ? out_rot : out_x);
+  }
+  if (launches) *launches = 2 + nl;
   return 0;
 }
 

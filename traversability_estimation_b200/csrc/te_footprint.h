@@ -30,6 +30,9 @@ struct FootprintState {
   bool tile_attr = false;     // k_sweep_tile's dynamic shared-memory limit has been raised (a per-device function attribute)
   void* d_list = nullptr;    // work list of the cells whose predicates need the window / gap-walk code (word 0: length)
   size_t list_cap = 0;
+  void* d_poly[2] = {nullptr, nullptr};  // run / uncertain-offset tables of the unrotated and the rotated footprint polygon
+  size_t poly_cap[2] = {0, 0};
+  bool poly_attr = false;
   void invalidate() { valid = false; tables_valid = false; }
   void release();
 };
@@ -40,6 +43,12 @@ int launch_footprint(FootprintState& st, const SlabView& v, const te_geometry* g
                      const std::vector<double>& X, const std::vector<double>& Y, const float* trav, const float* slope,
                      const float* step, const float* rough, const float* elev, float* out, float* slope_fp, float* step_fp,
                      float* rough_fp, int sms, cudaStream_t s, int* launches);
+
+// TraversabilityMap::traversabilityFootprint(double footprintYaw) (TraversabilityMap.cpp:239-305): layers traversability_x / _rot.
+int footprint_polygon_halo(const te_geometry* g, const te_footprint_params* p, int npts, const double* pts_xy);
+int launch_footprint_polygon(FootprintState& st, const SlabView& v, const te_geometry* g, const te_footprint_params* p, int npts,
+                             const double* pts_xy, double yaw, const float* trav, const float* slope, const float* step,
+                             const float* rough, const float* elev, float* out_x, float* out_rot, int sms, cudaStream_t s, int* launches);
 
 // TraversabilityMap::checkCircularFootprintPath for a batch of paths on a complete traversability_footprint layer (device pointers).
 void launch_check_paths(const SlabView& v, const te_geometry* g, double traversability_default, const float* footprint, const float* robot_slope, int npaths,
