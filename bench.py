@@ -43,7 +43,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=400)   # >= 0.2 s of timed device work at 8192^2
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="chain8192", choices=["chain8192", "chain2048", "batched512", "footprint4096", "footprint4096_offset0", "slope8192", "plugin_chain"])
+    ap.add_argument("--workload", default="chain8192", choices=["chain8192", "chain2048", "batched512", "footprint4096", "footprint4096_offset0", "footprint_polygon4096", "slope8192", "plugin_chain"])
     ap.add_argument("--scaling", default="strong", choices=["weak", "strong"])
     ap.add_argument("--halo", default="ipc", choices=["ipc", "nccl"], help="halo exchange at N>1: peer-mapped pull (C ABI) or NCCL send/recv")
     ap.add_argument("--halo-overlap", type=int, default=1, help="N>1, --halo ipc: pull the halo of the NEXT buffer set on a side stream while the chain runs on the current one (0: inline, on the chain's stream)")
@@ -335,6 +335,14 @@ def run_other(args, torch, dist, te, world, rank, local, dev):
 
         def step():
             ctx.footprint(g, fp, lay[3], lay[0], lay[1], z, out, te.MEM_DEVICE)
+        if args.workload == "footprint_polygon4096":
+            # traversabilityFootprint(yaw) with the YAML footprint (robot_footprint_parameter.yaml:3) and yaw (robot.yaml:9): two layers
+            poly = [[0.45, 0.30], [0.45, -0.30], [-0.45, -0.30], [-0.45, 0.30]]
+            out2 = torch.empty((cols, rows), dtype=torch.float32, device=dev)
+            name = f"polygon footprint sweep (0.9 m x 0.6 m, yaw 0.7854: traversability_x + traversability_rot) over {rows}x{cols}"
+
+            def step():  # noqa: F811
+                ctx.footprint_polygon(g, fp, poly, 0.7854, lay[3], lay[0], lay[1], z, out, out2, te.MEM_DEVICE)
 
     def barrier():
         if world > 1:
@@ -358,7 +366,7 @@ def run_other(args, torch, dist, te, world, rank, local, dev):
     l1, _ = ctx.stats()
     if rank == 0:
         peak, src = measured_peak()
-        bpc = 8 if args.workload == "slope8192" else ALG_BYTES_PER_CELL
+        bpc = 8 if args.workload == "slope8192" else (24 if args.workload == "footprint_polygon4096" else ALG_BYTES_PER_CELL)
         ach = bpc * (cells / world) / (ms / args.steps * 1e-3) / 1e9
         print(json.dumps({"metric": "Mcells/s " + {"batched512": "full filter chain", "slope8192": "slope filter"}.get(args.workload, "footprint sweep") + ", synthetic elevation",
                           "value": cells * args.steps / (ms * 1e-3) / 1e6, "unit": "Mcells/s", "n_gpus": world, "steps": args.steps,
@@ -396,7 +404,7 @@ def main():
     if args.workload == "plugin_chain":
         assert world == 1
         return run_plugin_chain(args, torch, dev)
-    if args.workload in ("batched512", "footprint4096", "footprint4096_offset0", "slope8192"):
+    if args.workload in ("batched512", "footprint4096", "footprint4096_offset0", "footprint_polygon4096", "slope8192"):
         return run_other(args, torch, dist, te, world, rank, local, dev)
     rows = args.rows or {"chain8192": 8192, "chain2048": 2048}.get(args.workload, 8192)
     base_cols = args.cols or rows
