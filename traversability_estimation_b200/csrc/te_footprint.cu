@@ -58,6 +58,9 @@ struct FpArgs {
   // centre's own entry P[column j][row i], of the two ends of disk column l (index l + L), and the running cell count
   int off_hi[64], off_lo[64];
   short cntp[65];
+  // the same for k_sweep_fast as non-negative BYTE offsets from the prefix entry L columns and L rows before the centre's own
+  // (one 32-bit add to a 64-bit base per load instead of a sign-extended 64-bit index computation)
+  unsigned off8_hi[64], off8_lo[64];
 };
 
 __device__ __forceinline__ float lay(const FpArgs& A, const float* l, int i, int j) {  // caller guarantees (i,j) is in the map
@@ -440,12 +443,11 @@ __global__ void __launch_bounds__(256) k_sweep_fast(FpArgs A, Layers L, const un
     //      a few words per column, shared by the 32 centres)  Mostly not: then no lane has anything to look for.
     bool warp_any;
     {
-      const int w0 = max(i0 - A.L, 0) >> 5, w1 = min(i0 + 31 + A.L, A.rows - 1) >> 5, nw = w1 - w0 + 1;
-      const int ne = (l_hi - l_lo + 1) * nw;
+      const int w0 = max(i0 - A.L, 0) >> 5, w1 = min(i0 + 31 + A.L, A.rows - 1) >> 5;
       unsigned acc = 0;
-      for (int e = lane; e < ne; e += 32) {
-        const int l = l_lo + e / nw, w = w0 + e % nw;
-        acc |= __ldg(A.bits + (size_t)(j + l - A.in_col0) * A.words + w);
+      for (int l = l_lo + lane; l <= l_hi; l += 32) {  // a lane per disk column, at most four words each
+        const unsigned* wc = A.bits + (size_t)(j + l - A.in_col0) * A.words;
+        for (int w = w0; w <= w1; ++w) acc |= __ldg(wc + w);
       }
       warp_any = __any_sync(0xffffffffu, acc != 0u);
     }
@@ -485,14 +487,17 @@ __global__ void __launch_bounds__(256) k_sweep_fast(FpArgs A, Layers L, const un
     if (!warp_any && i - A.L >= 0 && i + A.L < A.rows) {
       // nothing blocked near this warp and no clipping along the rows: 2 loads and 2 additions per disk column, offsets from
       // the constant bank
-      const double* pc0 = A.P + (size_t)(j - A.in_col0) * ((size_t)A.rows + 1) + i;
+      // biased base: the entry L columns and L rows before the centre's own, so that every table offset is a non-negative byte count
+      const char* pb = reinterpret_cast<const char*>(A.P + ((size_t)(j - A.in_col0) * ((size_t)A.rows + 1) + i)) -
+                       8 * ((ptrdiff_t)A.L * ((ptrdiff_t)A.rows + 1) + A.L);
+      auto P8 = [&](unsigned off) { return __ldg(reinterpret_cast<const double*>(pb + off)); };
       int l = l_lo + A.L;
       const int l_end = l_hi + A.L;
       for (; l + 1 <= l_end; l += 2) {
-        t += pc0[A.off_hi[l]] - pc0[A.off_lo[l]];
-        t_b += pc0[A.off_hi[l + 1]] - pc0[A.off_lo[l + 1]];
+        t += P8(A.off8_hi[l]) - P8(A.off8_lo[l]);
+        t_b += P8(A.off8_hi[l + 1]) - P8(A.off8_lo[l + 1]);
       }
-      if (l <= l_end) t += pc0[A.off_hi[l]] - pc0[A.off_lo[l]];
+      if (l <= l_end) t += P8(A.off8_hi[l]) - P8(A.off8_lo[l]);
       t += t_b;
       n = (int)A.cntp[l_end + 1] - (int)A.cntp[l_lo + A.L];
     } else {
@@ -802,7 +807,9 @@ struct PolyArgs {
   int Lp;             // reach of the polygon in cells (<= 31)
   int nruns, nfz, npts;
   const int* runs;    // (dj & 0xff) | (lo & 0xff) << 8 | (hi & 0xff) << 16: rows i+lo .. i+hi of column j+dj are certainly inside
-  const int* fz;      // (di & 0xff) | (dj & 0xff) << 8 | flags << 16: uncertain offsets; flag bit 0: depends on the centre's row
+  const int* fz;      // (di & 0xff) | (dj & 0xff) << 8 | flags << 16: uncertain offsets, sorted by (dj, di); flag bit 0: the decision
+                      // depends on the centre's row; bit 1: same column as the previous entry, next row, neither depends on the row
+  int ncert;          // number of certain cells (sum of the run lengths)
   double r00, r01, r10, r11;  // Eigen::Quaternion::toRotationMatrix of (cos(yaw/2), 0, 0, sin(yaw/2)), upper-left 2 x 2
   double px[PMAXV], py[PMAXV];
 };
@@ -826,10 +833,9 @@ __device__ bool poly_inside_d(const PolyArgs& Q, double cx, double cy, double pt
 
 __global__ void __launch_bounds__(256) k_poly_tile(FpArgs A, PolyArgs Q, const float* __restrict__ trav, const unsigned char* __restrict__ blocked,
                                                    float* __restrict__ out) {
-  extern __shared__ double sP[];  // [NC][PS] prefix sums of t'; then [NC][PB] uint16 prefix counts of blocked; then [NC][128] blocked bytes
+  extern __shared__ double sP[];  // [NC][PS] prefix sums of t'; then [NC][PB] uint16 prefix counts of blocked cells
   const int Lr = Q.Lp, NR = PTR + 2 * Lr, NC = PTC + 2 * Lr, PS = NR + 1;
   unsigned short* sB = reinterpret_cast<unsigned short*>(sP + (size_t)NC * PS);
-  unsigned char* sBlk = reinterpret_cast<unsigned char*>(sB + (size_t)NC * PB);
   const int r0 = (int)blockIdx.x * PTR, c0 = A.out_col0 + (int)blockIdx.y * PTC;
   const int rb = r0 - Lr, cb = c0 - Lr;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -856,7 +862,6 @@ __global__ void __launch_bounds__(256) k_poly_tile(FpArgs A, PolyArgs Q, const f
       }
     }
     anyb |= (int)bw;
-    reinterpret_cast<unsigned*>(sBlk)[cc * 32 + lane] = bw;
     v[1] += v[0]; v[2] += v[1]; v[3] += v[2];
     cb4[1] += cb4[0]; cb4[2] += cb4[1]; cb4[3] += cb4[2];
     double tot = v[3];
@@ -895,23 +900,40 @@ __global__ void __launch_bounds__(256) k_poly_tile(FpArgs A, PolyArgs Q, const f
     double t = 0.0;
     int n = 0, nblk = 0;
     // certain cells: per-column runs from the prefix sums (cells outside the map were staged as t' = 0, not blocked)
-    for (int r = 0; r < Q.nruns; ++r) {
-      const int w = __ldg(Q.runs + r);
-      const int dj = (int)(signed char)(w & 0xff), lo = (int)(signed char)((w >> 8) & 0xff), hi = (int)(signed char)((w >> 16) & 0xff);
-      const int b = j + dj, lb = b - A.in_col0;
-      if (b < 0 || b >= A.cols_total || lb < 0 || lb >= A.in_ncols) continue;
-      const int a0 = max(ic + lo, 0), a1 = min(ic + hi, A.rows - 1);
-      if (a0 > a1) continue;
-      const int cc = b - cb;
-      const double* pc = sP + (size_t)cc * PS + k0;
-      t += pc[hi + 1] - pc[lo];
-      n += a1 - a0 + 1;
-      if (tile_any) {
-        const unsigned short* bc = sB + (size_t)cc * PB + k0;
-        nblk += (int)bc[hi + 1] - (int)bc[lo];
+    const double* pbase = sP + (size_t)(j - cb) * PS + k0;
+    const unsigned short* bbase = sB + (size_t)(j - cb) * PB + k0;
+    const bool interior = ic - Lr >= 0 && ic + Lr < A.rows && j - Lr >= max(0, A.in_col0) && j + Lr <= min(A.cols_total, A.in_col0 + A.in_ncols) - 1;
+    if (interior) {  // no clipping anywhere: the cell count is the table's
+      for (int r = 0; r < Q.nruns; ++r) {
+        const int w = __ldg(Q.runs + r);
+        const int dj = (int)(signed char)(w & 0xff), lo = (int)(signed char)((w >> 8) & 0xff), hi = (int)(signed char)((w >> 16) & 0xff);
+        const double* pc = pbase + dj * PS;
+        t += pc[hi + 1] - pc[lo];
+        if (tile_any) {
+          const unsigned short* bc = bbase + dj * PB;
+          nblk += (int)bc[hi + 1] - (int)bc[lo];
+        }
+      }
+      n = Q.ncert;
+    } else {
+      for (int r = 0; r < Q.nruns; ++r) {
+        const int w = __ldg(Q.runs + r);
+        const int dj = (int)(signed char)(w & 0xff), lo = (int)(signed char)((w >> 8) & 0xff), hi = (int)(signed char)((w >> 16) & 0xff);
+        const int b = j + dj, lb = b - A.in_col0;
+        if (b < 0 || b >= A.cols_total || lb < 0 || lb >= A.in_ncols) continue;
+        const int a0 = max(ic + lo, 0), a1 = min(ic + hi, A.rows - 1);
+        if (a0 > a1) continue;
+        const double* pc = pbase + dj * PS;
+        t += pc[hi + 1] - pc[lo];
+        n += a1 - a0 + 1;
+        if (tile_any) {
+          const unsigned short* bc = bbase + dj * PB;
+          nblk += (int)bc[hi + 1] - (int)bc[lo];
+        }
       }
     }
-    // uncertain offsets, 32 per pass: lane l decides offset base + l when the decision is the same for every row of the column
+    // uncertain offsets, 32 per pass: lane l decides offset base + l when the decision is the same for every row of the column; the
+    // offsets that came out inside and follow each other down a column are then summed as ONE run from the prefix sums
     for (int base = 0; base < Q.nfz; base += 32) {
       const int idx = base + lane;
       int w = 0;
@@ -929,19 +951,28 @@ __global__ void __launch_bounds__(256) k_poly_tile(FpArgs A, PolyArgs Q, const f
         }
       }
       unsigned m = __ballot_sync(0xffffffffu, cand);
+      const unsigned ext = m & __ballot_sync(0xffffffffu, ((w >> 17) & 1) != 0);  // inside AND continues its predecessor down the column
       while (m) {
         const int src = __ffs((int)m) - 1;
-        m &= m - 1;
+        const unsigned tail = src == 31 ? 0u : (ext >> (src + 1));
+        const int len = __ffs((int)~tail) - 1;  // further entries of the run (0..31 - src)
+        m &= ~((len >= 31 ? 0xffffffffu : ((2u << len) - 1u)) << src);
         const int wv = __shfl_sync(0xffffffffu, w, src);
         const int di = (int)(signed char)(wv & 0xff), dj = (int)(signed char)((wv >> 8) & 0xff);
-        const int a = ic + di, b = j + dj, lb = b - A.in_col0;
-        if (a < 0 || b < 0 || a >= A.rows || b >= A.cols_total || lb < 0 || lb >= A.in_ncols) continue;
-        if (((wv >> 16) & 1) && !poly_inside_d(Q, cx, cy, A.X[a], A.Y[b])) continue;
-        const int cc = b - cb, kk = a - rb;
-        if (sBlk[cc * 128 + kk]) { ++nblk; continue; }
-        const double* pc = sP + (size_t)cc * PS + kk;
-        t += pc[1] - pc[0];
-        ++n;
+        const int b = j + dj, lb = b - A.in_col0;
+        if (b < 0 || b >= A.cols_total || lb < 0 || lb >= A.in_ncols) continue;
+        const int a0 = ic + di, a1 = a0 + len;
+        const int a0c = max(a0, 0), a1c = min(a1, A.rows - 1);
+        if (a0c > a1c) continue;
+        if (((wv >> 16) & 1) && !poly_inside_d(Q, cx, cy, A.X[a0], A.Y[b])) continue;  // row-dependent entries never chain (len == 0)
+        const int cc = b - cb;
+        const double* pc = sP + (size_t)cc * PS + (a0 - rb);
+        t += pc[len + 1] - pc[0];
+        n += a1c - a0c + 1;
+        if (tile_any) {
+          const unsigned short* bc = sB + (size_t)cc * PB + (a0 - rb);
+          nblk += (int)bc[len + 1] - (int)bc[0];
+        }
       }
     }
     if (!active) continue;
@@ -1286,6 +1317,9 @@ int launch_footprint(FootprintState& st, const SlabView& v, const te_geometry* g
       const int l = k - st.L, h = (k <= 2 * st.L) ? (int)st.h_halfw[k] : -1;
       a.off_hi[k] = h >= 0 ? l * pstride + h + 1 : 0;
       a.off_lo[k] = h >= 0 ? l * pstride - h : 0;   // a column outside the disk contributes P[0] - P[0]
+      const long long bias = (long long)st.L * pstride + st.L;
+      a.off8_hi[k] = (unsigned)(8 * (bias + a.off_hi[k]));
+      a.off8_lo[k] = (unsigned)(8 * (bias + a.off_lo[k]));
       a.cntp[k + 1] = (short)(a.cntp[k] + (h >= 0 ? 2 * h + 1 : 0));
     }
   }
@@ -1362,7 +1396,12 @@ bool classify_polygon(double res, int Lp, int npts, const double* px, const doub
       }
       if (fuzzy) {
         if (out->fz.size() >= 4096) { *why = "footprint polygon has more than 4096 cells on its outline"; return false; }
-        out->fz.push_back((di & 0xff) | ((dj & 0xff) << 8) | ((row_dep ? 1 : 0) << 16));
+        int chain = 0;
+        if (!row_dep && !out->fz.empty()) {
+          const int pw = out->fz.back();
+          if ((int)(signed char)((pw >> 8) & 0xff) == dj && (int)(signed char)(pw & 0xff) == di - 1 && ((pw >> 16) & 1) == 0) chain = 1;
+        }
+        out->fz.push_back((di & 0xff) | ((dj & 0xff) << 8) | ((row_dep ? 1 : 0) << 16) | (chain << 17));
         inside = false;
       }
       if (inside && !in_run) { in_run = true; run_lo = di; }
@@ -1385,9 +1424,9 @@ int launch_footprint_polygon(FootprintState& st, const SlabView& v, const te_geo
   if (Lp > 31) { st.why = "footprint polygon reaches further than 31 cells from its centre"; return TE_ERR_UNSUPPORTED; }
   FpArgs a{};
   if (int rc = run_predicates(st, v, g, p, trav, slope, step, rough, elev, nullptr, nullptr, nullptr, sms, s, &a)) return rc;
-  const size_t smem = sizeof(double) * (size_t)(PTC + 2 * Lp) * (PTR + 2 * Lp + 1) + (size_t)(PTC + 2 * Lp) * (PB * 2 + 128);
+  const size_t smem = sizeof(double) * (size_t)(PTC + 2 * Lp) * (PTR + 2 * Lp + 1) + (size_t)(PTC + 2 * Lp) * (PB * 2);
   if (!st.poly_attr) {
-    const size_t smax = sizeof(double) * (size_t)(PTC + 62) * (PTR + 63) + (size_t)(PTC + 62) * (PB * 2 + 128);
+    const size_t smax = sizeof(double) * (size_t)(PTC + 62) * (PTR + 63) + (size_t)(PTC + 62) * (PB * 2);
     if (cudaFuncSetAttribute(k_poly_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smax) != cudaSuccess) {
       st.why = "cudaFuncSetAttribute(max dynamic shared memory) failed"; return TE_ERR_CUDA;
     }
@@ -1417,6 +1456,8 @@ int launch_footprint_polygon(FootprintState& st, const SlabView& v, const te_geo
     if (!tb.runs.empty() && cudaMemcpyAsync(dr, tb.runs.data(), sizeof(int) * tb.runs.size(), cudaMemcpyHostToDevice, s) != cudaSuccess) { st.why = "polygon table upload failed"; return TE_ERR_CUDA; }
     if (!tb.fz.empty() && cudaMemcpyAsync(df, tb.fz.data(), sizeof(int) * tb.fz.size(), cudaMemcpyHostToDevice, s) != cudaSuccess) { st.why = "polygon table upload failed"; return TE_ERR_CUDA; }
     q.runs = dr; q.fz = df; q.nruns = (int)tb.runs.size(); q.nfz = (int)tb.fz.size();
+    q.ncert = 0;
+    for (int rw : tb.runs) q.ncert += (int)(signed char)((rw >> 16) & 0xff) - (int)(signed char)((rw >> 8) & 0xff) + 1;
     k_poly_tile<<<dim3((unsigned)((v.rows + PTR - 1) / PTR), (unsigned)((v.out_ncols + PTC - 1) / PTC)), 256, smem, s>>>(
         a, q, trav, (const unsigned char*)st.d_block, which ? out_rot : out_x);
   }
