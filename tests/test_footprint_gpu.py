@@ -223,3 +223,29 @@ def test_polygon_footprint_sweep_matches_oracle(te, ctx, oracle, case):
     assert (rx == 0).any() and (rx > 0).any() and (rrot > 0).any()
     if case["yaw"] != 0.0:
         assert not np.array_equal(rx, rrot)
+
+
+def test_polygon_footprint_slabs_equal_whole_map(te, ctx, oracle):
+    """Multi-GPU tiling of the polygon sweep: a column slab with its halo gives exactly the whole-map layers."""
+    import torch
+    rows, cols = 128, 300
+    z = synth.terrain(rows, cols, 0.02, 43, "mixed")
+    og = oracle.Geometry.make(rows, cols, 0.02)
+    g = te.Geometry.make(rows, cols, 0.02)
+    ch = oracle.chain(og, oracle.ChainParams.yaml_defaults(0), z)
+    fp = te.FootprintParams.yaml_defaults()
+    poly = [[0.45, 0.30], [0.45, -0.30], [-0.45, -0.30], [-0.45, 0.30]]
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(np.asarray(a, dtype=np.float32).T)).cuda()  # noqa: E731
+    lay = [dev(ch["traversability"]), dev(ch["slope"]), dev(ch["step"]), dev(z)]
+    ctx.set_stream(None)
+    wx, wr = (torch.empty((cols, rows), dtype=torch.float32, device="cuda") for _ in range(2))
+    ctx.footprint_polygon(g, fp, poly, 0.7854, *lay, wx, wr, te.MEM_DEVICE)
+    ctx.synchronize()
+    H = 29 + 20   # reach of the polygon (0.541 m -> 28 + 1 cells) + the predicates' halo
+    for b, e in ((0, 150), (150, 300)):
+        hl, hr = min(H, b), min(H, cols - e)
+        part = [x[b - hl:e + hr].contiguous() for x in lay]
+        ox, orr = (torch.empty((e - b, rows), dtype=torch.float32, device="cuda") for _ in range(2))
+        ctx.footprint_polygon(g, fp, poly, 0.7854, *part, ox, orr, te.MEM_DEVICE, slab=te.Slab(b, e - b, hl, hr))
+        ctx.synchronize()
+        assert torch.equal(wx[b:e], ox) and torch.equal(wr[b:e], orr), (b, e)
