@@ -189,7 +189,7 @@ __device__ __forceinline__ f2 negf2(f2 a) { return mk(-lo(a), -hi(a)); }
 // (N^2 - m^2) / (N (N + m)); no cancellation, relative error of s ~4.5e-7 from MUFU.SQRT and MUFU.RCP) instead of the
 // series in tan^2 below 0.05 rad / a Newton-corrected rsqrt above: six packed instructions, two selects and two compares less.
 #ifndef TE_MATH2
-#define TE_MATH2 0
+#define TE_MATH2 1
 #endif
 
 // Three-input min/max (FMNMX3) with IEEE minNum/maxNum semantics: NaN operands are skipped, which is
