@@ -97,6 +97,7 @@ struct te_ctx {
   // NEXT call, so a call needs no cudaMemsetAsync of its own (one stream operation and one launch gap less per map).
   int counter_phase = 0;    // block of the most recent fused launch (what the statistics entry points read)
   int counter_clean = -1;   // block known to be zero on the stream (-1: none)
+  cudaStream_t counter_stream = nullptr;  // the stream whose order that knowledge belongs to
   te::FusedState fused;      // tensor maps / tables of the fused stencil
   te::FootprintState fp;
 
@@ -287,6 +288,8 @@ int run_chain_device(te_ctx* c, const te_geometry* g, const te::SlabView& v, con
       const int phase = c->counter_phase ^ 1;
       unsigned* const cnt = (unsigned*)c->counter.p + 128 * phase;
       unsigned* const cnt_next = (unsigned*)c->counter.p + 128 * (phase ^ 1);
+      if (c->counter_stream != c->stream) c->counter_clean = -1;  // zeroed in another stream's order: not ordered before this launch
+      c->counter_stream = c->stream;
       if (c->counter_clean != phase) TE_CUDA(cudaMemsetAsync(cnt, 0, sizeof(unsigned) * 128, c->stream));
       c->counter_clean = -1;
       c->counter_phase = phase;
