@@ -103,6 +103,15 @@ __device__ __forceinline__ float acos_t2(float x) {
 // `why` receives the reason of an escalation (1 degenerate full window, 2 rank of a full window, 3 eigen-gap of a full window,
 // 4 no convergence, 5 rank of a partial window, 6 conditioning of a partial window, 7 null eigenvector, 8 n_z == 0,
 // 9 n_z on a float32 rounding boundary) in its low byte and the number of valid window cells in the next one.
+// SHAPE: the window's cells as a 25-bit mask (bit (l+2)*5 + (k+2)) known at compile time — the two shapes the fused stencil is
+// instantiated for — so that cells outside the disk cost nothing (no load, no select, no bit test); 0 = take it from A.wn.
+constexpr unsigned shape_mask(int w0, int w1, int w2) {
+  auto col = [](int w) { return w >= 2 ? 0x1fu : w == 1 ? 0x0eu : w == 0 ? 0x04u : 0u; };
+  return (col(w2)) | (col(w1) << 5) | (col(w0) << 10) | (col(w1) << 15) | (col(w2) << 20);
+}
+constexpr unsigned SHAPE_A = shape_mask(2, 2, 1), SHAPE_B = shape_mask(1, 1, -1);
+
+template <unsigned SHAPE>
 __device__ bool normals_t2(const FixupArgs& A, const Elev& E, int i, int j, float& fnx, float& fny, float& fnz, float& slope,
                            float& rough, unsigned& why) {
   const float zc = E(i, j);
@@ -118,11 +127,13 @@ __device__ bool normals_t2(const FixupArgs& A, const Elev& E, int i, int j, floa
   {
     const int lb0 = j - A.in_col0;
     const double dzc = (double)zc;
-    unsigned shape = 0;  // cells of the disk window
+    unsigned shape = SHAPE;  // cells of the disk window
+    if (SHAPE == 0u) {
 #pragma unroll
-    for (int l = -2; l <= 2; ++l) {
-      const int w = A.wn[l < 0 ? -l : l];
-      shape |= (w >= 2 ? 0x1fu : w == 1 ? 0x0eu : w == 0 ? 0x04u : 0u) << ((l + 2) * 5);
+      for (int l = -2; l <= 2; ++l) {
+        const int w = A.wn[l < 0 ? -l : l];
+        shape |= (w >= 2 ? 0x1fu : w == 1 ? 0x0eu : w == 0 ? 0x04u : 0u) << ((l + 2) * 5);
+      }
     }
     float v[5][5];
     if (i >= 2 && i + 2 < A.rows && j >= 2 && j + 2 < A.cols_total && lb0 >= 2 && lb0 + 2 < A.in_ncols) {
@@ -130,7 +141,8 @@ __device__ bool normals_t2(const FixupArgs& A, const Elev& E, int i, int j, floa
 #pragma unroll
       for (int l = -2; l <= 2; ++l)
 #pragma unroll
-        for (int k = -2; k <= 2; ++k) v[l + 2][k + 2] = __ldg(base + (ptrdiff_t)l * A.rows + k);
+        for (int k = -2; k <= 2; ++k)
+          v[l + 2][k + 2] = (SHAPE == 0u || ((SHAPE >> ((l + 2) * 5 + (k + 2))) & 1u)) ? __ldg(base + (ptrdiff_t)l * A.rows + k) : 0.0f;
     } else {
 #pragma unroll
       for (int l = -2; l <= 2; ++l) {
@@ -140,6 +152,7 @@ __device__ bool normals_t2(const FixupArgs& A, const Elev& E, int i, int j, floa
 #pragma unroll
         for (int k = -2; k <= 2; ++k) {
           const int a = i + k;
+          if (SHAPE != 0u && !((SHAPE >> ((l + 2) * 5 + (k + 2))) & 1u)) { v[l + 2][k + 2] = 0.0f; continue; }
           const float x = __ldg(col + min(max(a, 0), A.rows - 1));
           v[l + 2][k + 2] = (col_ok && a >= 0 && a < A.rows) ? x : nanf_();
         }
@@ -151,6 +164,7 @@ __device__ bool normals_t2(const FixupArgs& A, const Elev& E, int i, int j, floa
 #pragma unroll
       for (int k = -2; k <= 2; ++k) {
         const unsigned bitm = 1u << ((l + 2) * 5 + (k + 2));
+        if (SHAPE != 0u && !(SHAPE & bitm)) continue;  // not a cell of the window: folded away after unrolling
         const bool ok = finitef(v[l + 2][k + 2]) && (shape & bitm) != 0u;
         mask |= ok ? bitm : 0u;
         const double d = (double)(ok ? v[l + 2][k + 2] : zc) - dzc;  // invalid cells: exact zero
@@ -179,7 +193,6 @@ __device__ bool normals_t2(const FixupArgs& A, const Elev& E, int i, int j, floa
                   4 * (__popc(mask & kl_p4) - __popc(mask & kl_m4));
   const double res2 = A.res * A.res;
   const int cnt = __popc(mask);
-  const double n = (double)cnt;
   const double su = -A.res * (double)ik, sv = -A.res * (double)il;
   const double suu = res2 * (double)ikk, svv = res2 * (double)ill, suv = res2 * (double)ikl;
   double nx = 0.0, ny = 0.0, nz = 1.0;
@@ -281,6 +294,7 @@ __device__ bool normals_t2(const FixupArgs& A, const Elev& E, int i, int j, floa
   return true;
 }
 
+template <unsigned SHAPE>
 __global__ void __launch_bounds__(128, 8) k_fixup_t2(FixupArgs A, const float* __restrict__ elev, ChainOut o,
                                                   const unsigned* __restrict__ list, const unsigned* __restrict__ count,
                                                   unsigned cap, unsigned* list3, unsigned* count3, unsigned cap3) {
@@ -302,7 +316,7 @@ __global__ void __launch_bounds__(128, 8) k_fixup_t2(FixupArgs A, const float* _
     unsigned why = 0;
     if (do_n) {
       float fx, fy, fz;
-      if (normals_t2(A, E, i, j, fx, fy, fz, s, r, why)) {
+      if (normals_t2<SHAPE>(A, E, i, j, fx, fy, fz, s, r, why)) {
         o.slope[c] = s;
         o.rough[c] = r;
         if (o.nx) { o.nx[c] = fx; o.ny[c] = fy; o.nz[c] = fz; }
@@ -347,7 +361,10 @@ void launch_fixup_t2(const FixupArgs& a, const float* elev, const ChainOut& o, c
   at.val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = &at;
   cfg.numAttrs = pdl ? 1 : 0;
-  cudaLaunchKernelEx(&cfg, k_fixup_t2, a, elev, o, list, count, cap, list3, count3, cap3);
+  const bool is_a = a.wn[0] == 2 && a.wn[1] == 2 && a.wn[2] == 1, is_b = a.wn[0] == 1 && a.wn[1] == 1 && a.wn[2] == -1;
+  if (is_a) cudaLaunchKernelEx(&cfg, k_fixup_t2<SHAPE_A>, a, elev, o, list, count, cap, list3, count3, cap3);
+  else if (is_b) cudaLaunchKernelEx(&cfg, k_fixup_t2<SHAPE_B>, a, elev, o, list, count, cap, list3, count3, cap3);
+  else cudaLaunchKernelEx(&cfg, k_fixup_t2<0u>, a, elev, o, list, count, cap, list3, count3, cap3);
 }
 
 }  // namespace te

@@ -969,6 +969,19 @@ void plan_levels(FusedArgs& a, int out_ncols, int nmaps, int total_warps) {
   int len[NLVL] = {len0, std::max(16, len0 * 3 / 8 / 8 * 8), 16, 16};
   double frac[NLVL] = {0.80, 0.15, 0.05, 0.0};
   if (len0 == 16) { frac[0] = 1.0; frac[1] = frac[2] = 0.0; }
+  if (share >= 400.0 && (long long)a.nstrips * nmaps <= total_warps / 4) {
+    // Large single maps: ONE long unit per warp first — as many segments per strip as give every warp (at most) one unit, over
+    // three quarters of the columns, so that a warp pays its 8 warm-up columns once for most of its work — then the tapering
+    // tail (24- and 16-column segments) that evens out the warps' different speeds.  8192^2: 12 segments of 512 columns per
+    // strip (1 644 units on 1 776 warps), measured 0.553 ms against 0.564 ms with 80-column segments (profiles/README.md).
+    const int nseg0 = (int)(total_warps / ((long long)a.nstrips * nmaps));
+    const int l0 = (int)(0.75 * out_ncols / nseg0) / 8 * 8;
+    if (l0 >= 128) {
+      len[0] = l0; len[1] = 24; len[2] = 16;
+      frac[0] = (double)l0 * nseg0 / out_ncols; frac[1] = 0.20; frac[2] = 1.0 - frac[0] - frac[1];
+      if (frac[2] < 0.0) { frac[1] = 1.0 - frac[0]; frac[2] = 0.0; }
+    }
+  }
   if (share < 100.0) {
     // Small launches (a warp's share is a couple of units at most): the tapering queue has nothing to balance and the whole-unit
     // quantisation decides — the kernel lasts rounds(len) units of len full march steps + 8 warm-up steps (which skip the later
