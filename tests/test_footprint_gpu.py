@@ -249,3 +249,34 @@ def test_polygon_footprint_slabs_equal_whole_map(te, ctx, oracle):
         ctx.footprint_polygon(g, fp, poly, 0.7854, *part, ox, orr, te.MEM_DEVICE, slab=te.Slab(b, e - b, hl, hr))
         ctx.synchronize()
         assert torch.equal(wx[b:e], ox) and torch.equal(wr[b:e], orr), (b, e)
+
+
+def test_polygon_footprint_with_roughness_check_and_argument_errors(te, ctx, oracle):
+    """verify_roughness_footprint in the polygon sweep (isTraversableForFilters :779-783) and the argument checks of the entry."""
+    rows, cols, res = 128, 120, 0.03
+    z = synth.terrain(rows, cols, res, 71, "mixed")
+    og, g = oracle.Geometry.make(rows, cols, res), te.Geometry.make(rows, cols, res)
+    ch = oracle.chain(og, oracle.ChainParams.yaml_defaults(0), z)
+    fo, ft = oracle.FootprintParams.yaml_defaults(), te.FootprintParams.yaml_defaults()
+    fo.verify_roughness = ft.verify_roughness = 1
+    poly = [[0.45, 0.30], [0.45, -0.30], [-0.45, -0.30], [-0.45, 0.30]]
+    lay = [np.asfortranarray(x, dtype=np.float32) for x in (ch["traversability"], ch["slope"], ch["step"], z)]
+    rough = np.asfortranarray(ch["roughness"], dtype=np.float32)
+    rx, rrot = oracle.footprint_polygon(og, fo, poly, 0.5, *lay, roughness=rough)
+    ox, orot = np.empty_like(lay[0]), np.empty_like(lay[0])
+    ctx.footprint_polygon(g, ft, poly, 0.5, *lay, ox, orot, te.MEM_HOST, roughness=rough)
+    assert np.array_equal(ox == 0, rx == 0) and np.array_equal(orot == 0, rrot == 0)
+    assert _close(ox, rx) and _close(orot, rrot)
+    fo.verify_roughness = 0
+    nx, _ = oracle.footprint_polygon(og, fo, poly, 0.5, *lay)
+    assert (rx == 0).sum() >= (nx == 0).sum()                           # the extra predicate can only block more
+    with pytest.raises(te.TEError) as err:                               # the flag without the layer
+        ctx.footprint_polygon(g, ft, poly, 0.5, *lay, ox, orot, te.MEM_HOST)
+    assert err.value.code == -2
+    ft.verify_roughness = 0
+    with pytest.raises(te.TEError) as err:                               # a polygon needs three vertices
+        ctx.footprint_polygon(g, ft, poly[:2], 0.5, *lay, ox, orot, te.MEM_HOST)
+    assert err.value.code == -1
+    with pytest.raises(te.TEError) as err:                               # reach beyond 31 cells: not supported, said so
+        ctx.footprint_polygon(g, ft, [[1.2, 0.3], [1.2, -0.3], [-1.2, -0.3], [-1.2, 0.3]], 0.5, *lay, ox, orot, te.MEM_HOST)
+    assert err.value.code == -4
