@@ -160,3 +160,30 @@ def test_streaming_slope_filter_is_bit_identical_to_the_literal_expression(te, c
         same = (got.view(torch.int32) == ref.view(torch.int32)) | (torch.isnan(got) & torch.isnan(ref))
         # torch's acos on the CPU and CUDA's libdevice acos may differ in the last bit of the double: allow a handful of cells
         assert int((~same).sum()) <= 4, (crit, int((~same).sum()), got[~same][:5], ref[~same][:5])
+
+
+@pytest.mark.parametrize("rows,cols,sr,sc", [(192, 160, 37, 101), (128, 96, 0, 5), (128, 96, 127, 0), (2048, 2048, 1000, 77)])
+def test_circular_buffer_start_index_through_the_host_path(te, ctx, rows, cols, sr, sc):
+    """te_chain(TE_MEM_HOST) takes the layers of a moving (robot-centric) grid_map as stored — cell (i, j) at buffer
+    index ((i + start_row) % rows, (j + start_col) % cols) — and returns its layers in the same order; the copies to and from the
+    device unwrap and re-wrap (2048^2 goes through the pipelined chunked path).  Must equal the unwrapped map's result bitwise."""
+    z = synth.terrain(rows, cols, 0.02, 91, "mixed")
+    g0 = te.Geometry.make(rows, cols, 0.02)
+    p = te.ChainParams.yaml_defaults(0)
+    ctx.set_kernel(te.KERNEL_AUTO)
+    ctx.set_stream(None)
+    ref = ctx.chain_host(g0, p, z, with_normals=True)
+    gw = te.Geometry.make(rows, cols, 0.02)
+    gw.start_row, gw.start_col = sr, sc
+    stored = np.asfortranarray(np.roll(z, (sr, sc), axis=(0, 1)))        # stored[(i + sr) % rows, (j + sc) % cols] = z[i, j]
+    got = ctx.chain_host(gw, p, stored, with_normals=True)
+    for k, a in ref.items():
+        b = np.roll(got[k], (-sr, -sc), axis=(0, 1))
+        assert np.array_equal(np.isnan(a), np.isnan(b)), k
+        assert np.array_equal(a[~np.isnan(a)], b[~np.isnan(b)]), k
+    import torch
+    with pytest.raises(te.TEError) as err:                                # device memory has no circular-buffer form here
+        zd = torch.zeros((cols, rows), dtype=torch.float32, device="cuda")
+        outs = [torch.empty((cols, rows), dtype=torch.float32, device="cuda") for _ in range(4)]
+        ctx.chain(gw, p, zd, *outs, te.MEM_DEVICE)
+    assert err.value.code == -4

@@ -110,13 +110,17 @@ struct te_ctx {
 
 namespace {
 
-int check_geometry(const te_geometry* g) {
+int check_geometry(const te_geometry* g, bool allow_start_index = false) {
   if (!g) return fail(TE_ERR_BAD_ARG, "geometry is null");
   if (g->rows <= 0 || g->cols <= 0) return fail(TE_ERR_BAD_ARG, "map size must be positive (rows=%d cols=%d)", g->rows, g->cols);
   if (!(g->resolution > 0.0) || !std::isfinite(g->resolution)) return fail(TE_ERR_BAD_ARG, "resolution must be positive");
-  if (g->start_row != 0 || g->start_col != 0)
-    return fail(TE_ERR_UNSUPPORTED, "circular-buffer start index (%d,%d) != (0,0): call convertToDefaultStartIndex() first",
-                g->start_row, g->start_col);
+  if (g->start_row != 0 || g->start_col != 0) {
+    if (!allow_start_index)
+      return fail(TE_ERR_UNSUPPORTED, "circular-buffer start index (%d,%d) != (0,0): call convertToDefaultStartIndex() first",
+                  g->start_row, g->start_col);
+    if (g->start_row < 0 || g->start_row >= g->rows || g->start_col < 0 || g->start_col >= g->cols)
+      return fail(TE_ERR_BAD_ARG, "circular-buffer start index (%d,%d) outside the map", g->start_row, g->start_col);
+  }
   if ((long long)g->rows * g->cols > 0x7fffffffLL * 2) return fail(TE_ERR_UNSUPPORTED, "map has more than 2^32 cells");
   return TE_OK;
 }
@@ -626,9 +630,40 @@ int te_roughness(te_ctx* c, const te_geometry* g, const te_chain_params* p, cons
 
 // Host-memory chain on a large map: column chunks flow H2D -> kernels -> D2H on three streams so that the two PCIe
 // directions and the compute overlap (the transfers dominate: 20 B/cell over PCIe against 20 B/cell over HBM).
+// Columns [c0, c0 + n) of the map in DEFAULT order <-> a host layer stored as a grid_map circular buffer with start index
+// (sr, sc): cell (i, j) of the map lives at stored[((j + sc) % cols) * rows + (i + sr) % rows] (GridMap::getIndex... /
+// convertToDefaultStartIndex).  `dev` holds map column c at dev + (c - dev_col0) * rows.  Up to four 2-D copies;
+// one plain copy when nothing wraps.  This is what lets te_chain(TE_MEM_HOST) take the message / GridMap buffers of a moving
+// (robot-centric) map as they are, without an unwrapped host copy.
+static cudaError_t copy_wrapped(float* dev, int dev_col0, float* host, int rows, int cols, int sr, int sc, int c0, int n, bool to_device,
+                                cudaStream_t s) {
+  const size_t pitch = sizeof(float) * (size_t)rows;
+  int done = 0;
+  while (done < n) {
+    const int c = c0 + done, js = (c + sc) % cols;     // stored column of map column c
+    const int m = std::min(n - done, cols - js);       // columns until the stored index wraps
+    float* d = dev + (size_t)(c - dev_col0) * rows;
+    float* h = host + (size_t)js * rows;
+    // rows [0, rows - sr) of the map are stored rows [sr, rows); rows [rows - sr, rows) are stored rows [0, sr)
+    const int r1 = rows - sr;
+    cudaError_t e;
+    if (to_device) e = cudaMemcpy2DAsync(d, pitch, h + sr, pitch, sizeof(float) * (size_t)r1, m, cudaMemcpyHostToDevice, s);
+    else e = cudaMemcpy2DAsync(h + sr, pitch, d, pitch, sizeof(float) * (size_t)r1, m, cudaMemcpyDeviceToHost, s);
+    if (e != cudaSuccess) return e;
+    if (sr > 0) {
+      if (to_device) e = cudaMemcpy2DAsync(d + r1, pitch, h, pitch, sizeof(float) * (size_t)sr, m, cudaMemcpyHostToDevice, s);
+      else e = cudaMemcpy2DAsync(h, pitch, d + r1, pitch, sizeof(float) * (size_t)sr, m, cudaMemcpyDeviceToHost, s);
+      if (e != cudaSuccess) return e;
+    }
+    done += m;
+  }
+  return cudaSuccess;
+}
+
 static int chain_host_pipelined(te_ctx* c, const te_geometry* g, const te_slab& s, const te_chain_params* p, const float* elev,
-                                float* const host_out[7]) {
+                                float* const host_out[7], int sr = 0, int sc = 0) {
   const int rows = g->rows, need = chain_halo(g, p);
+  const bool wrapped = sr != 0 || sc != 0;  // only with the whole map (no slab): buffer column == map column
   const int in_cols = s.halo_left + s.col_count + s.halo_right;
   const size_t col_bytes = sizeof(float) * (size_t)rows;
   TE_CUDA(c->stage[0].reserve(col_bytes * in_cols));
@@ -678,8 +713,10 @@ static int chain_host_pipelined(te_ctx* c, const te_geometry* g, const te_slab& 
     // chunk k reads input-buffer columns [halo_left + off - need, halo_left + off + cnt + need)
     const int upto = std::min(in_cols, s.halo_left + off + cnt + need);
     if (upto > uploaded) {
-      cudaError_t e = cudaMemcpyAsync((char*)c->stage[0].p + col_bytes * uploaded, (const char*)elev + col_bytes * uploaded,
-                                      col_bytes * (upto - uploaded), cudaMemcpyHostToDevice, c->s_h2d);
+      cudaError_t e = wrapped ? copy_wrapped((float*)c->stage[0].p, 0, const_cast<float*>(elev), rows, g->cols, sr, sc, uploaded,
+                                             upto - uploaded, true, c->s_h2d)
+                              : cudaMemcpyAsync((char*)c->stage[0].p + col_bytes * uploaded, (const char*)elev + col_bytes * uploaded,
+                                                col_bytes * (upto - uploaded), cudaMemcpyHostToDevice, c->s_h2d);
       if (e != cudaSuccess) { rc = fail(TE_ERR_CUDA, "H2D chunk copy failed: %s", cudaGetErrorString(e)); break; }
       uploaded = upto;
     }
@@ -697,8 +734,9 @@ static int chain_host_pipelined(te_ctx* c, const te_geometry* g, const te_slab& 
     cudaStreamWaitEvent(c->s_d2h, done[k], 0);
     for (int l = 0; l < 7; ++l)
       if (host_out[l]) {
-        cudaError_t e = cudaMemcpyAsync(host_out[l] + (size_t)off * rows, dev_out[l] + (size_t)off * rows, col_bytes * cnt,
-                                        cudaMemcpyDeviceToHost, c->s_d2h);
+        cudaError_t e = wrapped ? copy_wrapped(dev_out[l], 0, host_out[l], rows, g->cols, sr, sc, off, cnt, false, c->s_d2h)
+                                : cudaMemcpyAsync(host_out[l] + (size_t)off * rows, dev_out[l] + (size_t)off * rows, col_bytes * cnt,
+                                                  cudaMemcpyDeviceToHost, c->s_d2h);
         if (e != cudaSuccess) { rc = fail(TE_ERR_CUDA, "D2H chunk copy failed: %s", cudaGetErrorString(e)); break; }
       }
   }
@@ -709,9 +747,18 @@ static int chain_host_pipelined(te_ctx* c, const te_geometry* g, const te_slab& 
   return rc;
 }
 
-static int chain_common(te_ctx* c, const te_geometry* g, const te_slab* slab, const te_chain_params* p, int nmaps, const float* elev,
+static int chain_common(te_ctx* c, const te_geometry* g_in, const te_slab* slab, const te_chain_params* p, int nmaps, const float* elev,
                         float* slope, float* step, float* rough, float* trav, float* nx, float* ny, float* nz, int memory) {
-  if (int rc = check_geometry(g)) return rc;
+  if (int rc = check_geometry(g_in, true)) return rc;
+  // A circular-buffer start index is honoured for whole host maps: the copies to and from the device unwrap / re-wrap the
+  // layers, the kernels always see the default order (positions depend on the unwrapped index only).
+  const int sr = g_in->start_row, sc = g_in->start_col;
+  const bool wrapped = sr != 0 || sc != 0;
+  if (wrapped && (memory != TE_MEM_HOST || slab != nullptr || nmaps != 1))
+    return fail(TE_ERR_UNSUPPORTED, "circular-buffer start index (%d,%d) != (0,0) is supported for whole maps in host memory only", sr, sc);
+  te_geometry g0 = *g_in;
+  g0.start_row = g0.start_col = 0;
+  const te_geometry* g = &g0;
   if (int rc = check_params(p)) return rc;
   if (nmaps <= 0) return fail(TE_ERR_BAD_ARG, "number of maps must be positive");
   if (!elev) return fail(TE_ERR_MISSING_LAYER, "layer elevation is missing");
@@ -725,10 +772,11 @@ static int chain_common(te_ctx* c, const te_geometry* g, const te_slab* slab, co
   const float* din = elev;
   float* host_out[7] = {slope, step, rough, trav, nx, ny, nz};
   if (memory == TE_MEM_HOST && nmaps == 1 && s.col_count >= 1024 && (size_t)g->rows * s.col_count >= ((size_t)1 << 22))
-    return chain_host_pipelined(c, g, s, p, elev, host_out);
+    return chain_host_pipelined(c, g, s, p, elev, host_out, sr, sc);
   if (memory == TE_MEM_HOST) {
     TE_CUDA(c->stage[0].reserve(in_bytes));
-    TE_CUDA(cudaMemcpyAsync(c->stage[0].p, elev, in_bytes, cudaMemcpyHostToDevice, c->stream));
+    if (wrapped) TE_CUDA(copy_wrapped((float*)c->stage[0].p, 0, const_cast<float*>(elev), g->rows, g->cols, sr, sc, 0, g->cols, true, c->stream));
+    else TE_CUDA(cudaMemcpyAsync(c->stage[0].p, elev, in_bytes, cudaMemcpyHostToDevice, c->stream));
     din = (const float*)c->stage[0].p;
     float** dev_out[7] = {&o.slope, &o.step, &o.rough, &o.trav, &o.nx, &o.ny, &o.nz};
     for (int k = 0; k < 7; ++k) {
@@ -741,7 +789,10 @@ static int chain_common(te_ctx* c, const te_geometry* g, const te_slab* slab, co
   if (memory == TE_MEM_HOST) {
     float* dev_out[7] = {o.slope, o.step, o.rough, o.trav, o.nx, o.ny, o.nz};
     for (int k = 0; k < 7; ++k)
-      if (host_out[k]) TE_CUDA(cudaMemcpyAsync(host_out[k], dev_out[k], out_bytes, cudaMemcpyDeviceToHost, c->stream));
+      if (host_out[k]) {
+        if (wrapped) TE_CUDA(copy_wrapped(dev_out[k], 0, host_out[k], g->rows, g->cols, sr, sc, 0, g->cols, false, c->stream));
+        else TE_CUDA(cudaMemcpyAsync(host_out[k], dev_out[k], out_bytes, cudaMemcpyDeviceToHost, c->stream));
+      }
     TE_CUDA(cudaStreamSynchronize(c->stream));
   }
   return TE_OK;

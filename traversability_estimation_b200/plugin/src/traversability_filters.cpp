@@ -249,10 +249,11 @@ using te_plugin::geometry_of;
 using te_plugin::ChainRegistry;
 
 namespace {
-// Emit a cached (unwrapped) layer into `dst`, the layer's storage in the possibly circular-buffered output map.
-void emit(const grid_map::GridMap& like, bool wrapped, const float* cached, float* dst) {
-  if (wrapped) te_plugin::scatter_back(like, cached, dst);
-  else std::memcpy(dst, cached, sizeof(float) * (size_t)like.getSize()(0) * like.getSize()(1));
+// Emit a cached layer into `dst`, the layer's storage in the output map.  The registry runs te_chain on the map AS STORED
+// (circular-buffer start index included: the C ABI unwraps and re-wraps in its copies), so the cached layer already has the
+// buffer order of the map it was computed from — no unwrapped host copy of a moving map, no scatter.
+void emit(const grid_map::GridMap& like, const float* cached, float* dst) {
+  std::memcpy(dst, cached, sizeof(float) * (size_t)like.getSize()(0) * like.getSize()(1));
 }
 }  // namespace
 
@@ -284,12 +285,13 @@ template <typename T>
 bool SlopeFilter<T>::update(const T& mapIn, T& mapOut) {
   mapOut = mapIn;
   mapOut.add(type_);  // NaN everywhere; cells without a surface normal keep it
-  const te_plugin::Unwrapped u(mapOut);
-  const float* nz = u.map().get("surface_normal_z").data();  // throws std::out_of_range like GridMap::at
-  if (const float* cached = ChainRegistry::instance().layer(ChainRegistry::kSlope, u.map())) {
-    emit(mapOut, u.wrapped, cached, mapOut.get(type_).data());
+  (void)mapOut.get("surface_normal_z");  // throws std::out_of_range like GridMap::at
+  if (const float* cached = ChainRegistry::instance().layer(ChainRegistry::kSlope, mapOut)) {
+    emit(mapOut, cached, mapOut.get(type_).data());
     return true;
   }
+  const te_plugin::Unwrapped u(mapOut);
+  const float* nz = u.map().get("surface_normal_z").data();
   te_ctx* ctx = device_.get();
   if (!ctx) return false;
   const te_geometry g = geometry_of(u.map());
@@ -357,12 +359,13 @@ template <typename T>
 bool StepFilter<T>::update(const T& mapIn, T& mapOut) {
   mapOut = mapIn;
   mapOut.add(type_);
-  const te_plugin::Unwrapped u(mapOut);
-  const float* elevation = u.map().get("elevation").data();
-  if (const float* cached = ChainRegistry::instance().layer(ChainRegistry::kStep, u.map())) {
-    emit(mapOut, u.wrapped, cached, mapOut.get(type_).data());
+  (void)mapOut.get("elevation");
+  if (const float* cached = ChainRegistry::instance().layer(ChainRegistry::kStep, mapOut)) {
+    emit(mapOut, cached, mapOut.get(type_).data());
     return true;
   }
+  const te_plugin::Unwrapped u(mapOut);
+  const float* elevation = u.map().get("elevation").data();
   te_ctx* ctx = device_.get();
   if (!ctx) return false;
   const te_geometry g = geometry_of(u.map());
@@ -418,15 +421,19 @@ template <typename T>
 bool RoughnessFilter<T>::update(const T& mapIn, T& mapOut) {
   mapOut = mapIn;
   mapOut.add(type_);
+  (void)mapOut.get("surface_normal_x");  // same order of look-ups (and of the exception for a missing layer) as before
+  (void)mapOut.get("elevation");
+  (void)mapOut.get("surface_normal_y");
+  (void)mapOut.get("surface_normal_z");
+  if (const float* cached = ChainRegistry::instance().layer(ChainRegistry::kRoughness, mapOut)) {
+    emit(mapOut, cached, mapOut.get(type_).data());
+    return true;
+  }
   const te_plugin::Unwrapped u(mapOut);
   const float* nx = u.map().get("surface_normal_x").data();
   const float* elevation = u.map().get("elevation").data();
   const float* ny = u.map().get("surface_normal_y").data();
   const float* nz = u.map().get("surface_normal_z").data();
-  if (const float* cached = ChainRegistry::instance().layer(ChainRegistry::kRoughness, u.map())) {
-    emit(mapOut, u.wrapped, cached, mapOut.get(type_).data());
-    return true;
-  }
   te_ctx* ctx = device_.get();
   if (!ctx) return false;
   const te_geometry g = geometry_of(u.map());
@@ -484,11 +491,12 @@ bool FusedTraversabilityFilter<T>::update(const T& mapIn, T& mapOut) {
   for (const char* l : kOut) mapOut.add(l);
   if (keepNormals_)
     for (const char* l : kNrm) mapOut.add(l);
-  const te_plugin::Unwrapped u(mapOut);
-  const float* elevation = u.map().get("elevation").data();
+  // The map is passed AS STORED: te_chain(TE_MEM_HOST) honours the circular-buffer start index in its copies to and from the
+  // device, so a moving (robot-centric) map needs neither an unwrapped host copy nor a scatter of the results.
+  const float* elevation = mapOut.get("elevation").data();  // throws std::out_of_range like GridMap::at
   te_ctx* ctx = device_.get();
   if (!ctx) return false;
-  const te_geometry g = geometry_of(u.map());
+  const te_geometry g = geometry_of(mapOut);
   te_chain_params p = te_plugin::yaml_defaults();
   p.normals_radius = normalsRadius_;
   p.slope_critical = slopeCritical_;
@@ -498,22 +506,13 @@ bool FusedTraversabilityFilter<T>::update(const T& mapIn, T& mapOut) {
   p.step_critical_cells = stepCells_;
   p.roughness_critical = roughCritical_;
   p.roughness_radius = roughRadius_;
-  grid_map::Matrix tmp[7];
   float* dst[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   for (int k = 0; k < 4; ++k) dst[k] = mapOut.get(kOut[k]).data();
   if (keepNormals_)
     for (int k = 0; k < 3; ++k) dst[4 + k] = mapOut.get(kNrm[k]).data();
-  if (u.wrapped)
-    for (int k = 0; k < 7; ++k)
-      if (dst[k]) { tmp[k] = grid_map::Matrix(g.rows, g.cols, 0.f); dst[k] = tmp[k].data(); }
   if (te_chain(ctx, &g, nullptr, &p, elevation, dst[0], dst[1], dst[2], dst[3], dst[4], dst[5], dst[6], TE_MEM_HOST) != TE_OK) {
     ROS_ERROR("FusedTraversabilityFilter: %s", te_last_error());
     return false;
-  }
-  if (u.wrapped) {
-    for (int k = 0; k < 4; ++k) te_plugin::scatter_back(mapOut, tmp[k].data(), mapOut.get(kOut[k]).data());
-    if (keepNormals_)
-      for (int k = 0; k < 3; ++k) te_plugin::scatter_back(mapOut, tmp[4 + k].data(), mapOut.get(kNrm[k]).data());
   }
   return true;
 }
