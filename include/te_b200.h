@@ -47,9 +47,10 @@ typedef struct te_geometry {
   double length_x, length_y;
   double position_x, position_y;
   int32_t start_row, start_col; /* grid_map circular-buffer start index (GridMap::getStartIndex): cell (i, j) is stored at buffer
-                                   index ((i + start_row) % rows, (j + start_col) % cols).  te_chain(TE_MEM_HOST) on a whole map
-                                   takes and returns layers in that order (the copies to and from the device unwrap / re-wrap);
-                                   every other entry point wants 0 (TE_ERR_UNSUPPORTED otherwise: convertToDefaultStartIndex) */
+                                   index ((i + start_row) % rows, (j + start_col) % cols).  te_chain, te_footprint(2) and
+                                   te_footprint_polygon with TE_MEM_HOST on a whole map (no slab) take and return layers in
+                                   that order (the copies to and from the device unwrap / re-wrap); everything else wants 0
+                                   (TE_ERR_UNSUPPORTED otherwise: convertToDefaultStartIndex) */
 } te_geometry;
 
 /* Column slab of a larger map (multi-GPU tiling, one slab per rank).  Inputs cover columns

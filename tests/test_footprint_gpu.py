@@ -280,3 +280,28 @@ def test_polygon_footprint_with_roughness_check_and_argument_errors(te, ctx, ora
     with pytest.raises(te.TEError) as err:                               # reach beyond 31 cells: not supported, said so
         ctx.footprint_polygon(g, ft, [[1.2, 0.3], [1.2, -0.3], [-1.2, -0.3], [-1.2, 0.3]], 0.5, *lay, ox, orot, te.MEM_HOST)
     assert err.value.code == -4
+
+
+def test_footprint_entries_take_circular_buffer_maps(te, ctx, oracle):
+    """te_footprint / te_footprint_polygon (TE_MEM_HOST, whole map) with a non-zero grid_map start index: layers in buffer order in,
+    layers in buffer order out, equal to the unwrapped map's result bitwise."""
+    rows, cols, sr, sc = 144, 120, 55, 97
+    z = synth.terrain(rows, cols, 0.02, 47, "mixed")
+    og = oracle.Geometry.make(rows, cols, 0.02)
+    ch = oracle.chain(og, oracle.ChainParams.yaml_defaults(0), z)
+    g0 = te.Geometry.make(rows, cols, 0.02)
+    gw = te.Geometry.make(rows, cols, 0.02)
+    gw.start_row, gw.start_col = sr, sc
+    fp = te.FootprintParams.yaml_defaults()
+    poly = [[0.45, 0.30], [0.45, -0.30], [-0.45, -0.30], [-0.45, 0.30]]
+    lay = [np.asfortranarray(x, dtype=np.float32) for x in (ch["traversability"], ch["slope"], ch["step"], z)]
+    wl = [np.asfortranarray(np.roll(x, (sr, sc), axis=(0, 1))) for x in lay]
+    ctx.set_stream(None)
+    ref, refw = np.empty_like(lay[0]), np.empty_like(lay[0])
+    ctx.footprint(g0, fp, *lay, ref, te.MEM_HOST)
+    ctx.footprint(gw, fp, *wl, refw, te.MEM_HOST)
+    assert _same(ref, np.roll(refw, (-sr, -sc), axis=(0, 1)))
+    px, pr, pxw, prw = (np.empty_like(lay[0]) for _ in range(4))
+    ctx.footprint_polygon(g0, fp, poly, 0.7854, *lay, px, pr, te.MEM_HOST)
+    ctx.footprint_polygon(gw, fp, poly, 0.7854, *wl, pxw, prw, te.MEM_HOST)
+    assert np.array_equal(px, np.roll(pxw, (-sr, -sc), axis=(0, 1))) and np.array_equal(pr, np.roll(prw, (-sr, -sc), axis=(0, 1)))

@@ -810,11 +810,18 @@ int te_chain_batched(te_ctx* c, const te_geometry* g, const te_chain_params* p, 
   return chain_common(c, g, nullptr, p, nmaps, elev, slope, step, rough, trav, nullptr, nullptr, nullptr, memory);
 }
 
-int te_footprint2(te_ctx* c, const te_geometry* g, const te_slab* slab, const te_footprint_params* p, const float* trav,
+int te_footprint2(te_ctx* c, const te_geometry* g_in, const te_slab* slab, const te_footprint_params* p, const float* trav,
                   const float* slope, const float* step, const float* rough, const float* elev, float* out, float* slope_fp,
                   float* step_fp, float* rough_fp, int memory) {
   TE_ENTER(c);
-  if (int rc = check_geometry(g)) return rc;
+  if (int rc = check_geometry(g_in, true)) return rc;
+  const int sr = g_in->start_row, sc = g_in->start_col;  // circular-buffer maps: whole host maps only, like te_chain
+  const bool wrapped = sr != 0 || sc != 0;
+  if (wrapped && (memory != TE_MEM_HOST || slab != nullptr))
+    return fail(TE_ERR_UNSUPPORTED, "circular-buffer start index (%d,%d) != (0,0) is supported for whole maps in host memory only", sr, sc);
+  te_geometry g0 = *g_in;
+  g0.start_row = g0.start_col = 0;
+  const te_geometry* g = &g0;
   if (!p) return fail(TE_ERR_BAD_ARG, "footprint parameters are null");
   if (!(p->radius >= 0.0) || !(p->offset >= 0.0)) return fail(TE_ERR_BAD_ARG, "footprint radius/offset must be >= 0");
   if (!trav) return fail(TE_ERR_MISSING_LAYER, "layer traversability is missing");
@@ -839,7 +846,8 @@ int te_footprint2(te_ctx* c, const te_geometry* g, const te_slab* slab, const te
     for (int k = 0; k < 5; ++k) {
       if (!in[k]) continue;
       TE_CUDA(c->stage[slot_in[k]].reserve(in_bytes));
-      TE_CUDA(cudaMemcpyAsync(c->stage[slot_in[k]].p, in[k], in_bytes, cudaMemcpyHostToDevice, c->stream));
+      if (wrapped) TE_CUDA(copy_wrapped((float*)c->stage[slot_in[k]].p, 0, const_cast<float*>(in[k]), g->rows, g->cols, sr, sc, 0, g->cols, true, c->stream));
+      else TE_CUDA(cudaMemcpyAsync(c->stage[slot_in[k]].p, in[k], in_bytes, cudaMemcpyHostToDevice, c->stream));
       in[k] = (const float*)c->stage[slot_in[k]].p;
     }
     for (int k = 0; k < 4; ++k) {
@@ -858,7 +866,10 @@ int te_footprint2(te_ctx* c, const te_geometry* g, const te_slab* slab, const te
   c->launches += nl;
   if (memory == TE_MEM_HOST) {
     for (int k = 0; k < 4; ++k)
-      if (host_o[k]) TE_CUDA(cudaMemcpyAsync(host_o[k], o[k], out_bytes, cudaMemcpyDeviceToHost, c->stream));
+      if (host_o[k]) {
+        if (wrapped) TE_CUDA(copy_wrapped(o[k], 0, host_o[k], g->rows, g->cols, sr, sc, 0, g->cols, false, c->stream));
+        else TE_CUDA(cudaMemcpyAsync(host_o[k], o[k], out_bytes, cudaMemcpyDeviceToHost, c->stream));
+      }
     TE_CUDA(cudaStreamSynchronize(c->stream));
   }
   return TE_OK;
@@ -868,7 +879,14 @@ int te_footprint_polygon(te_ctx* c, const te_geometry* g, const te_slab* slab, c
                          const double* pts_xy, double yaw, const float* trav, const float* slope, const float* step, const float* rough,
                          const float* elev, float* out_x, float* out_rot, int memory) {
   TE_ENTER(c);
-  if (int rc = check_geometry(g)) return rc;
+  if (int rc = check_geometry(g, true)) return rc;
+  const int sr = g->start_row, sc = g->start_col;  // circular-buffer maps: whole host maps only, like te_chain
+  const bool wrapped = sr != 0 || sc != 0;
+  if (wrapped && (memory != TE_MEM_HOST || slab != nullptr))
+    return fail(TE_ERR_UNSUPPORTED, "circular-buffer start index (%d,%d) != (0,0) is supported for whole maps in host memory only", sr, sc);
+  te_geometry g0 = *g;
+  g0.start_row = g0.start_col = 0;
+  g = &g0;
   if (!p) return fail(TE_ERR_BAD_ARG, "footprint parameters are null");
   if (npts < 3 || npts > 16 || !pts_xy) return fail(TE_ERR_BAD_ARG, "footprint polygon needs 3 to 16 vertices");
   if (!std::isfinite(yaw)) return fail(TE_ERR_BAD_ARG, "footprint yaw is not finite");
@@ -893,7 +911,8 @@ int te_footprint_polygon(te_ctx* c, const te_geometry* g, const te_slab* slab, c
     for (int k = 0; k < 5; ++k) {
       if (!in[k]) continue;
       TE_CUDA(c->stage[slot_in[k]].reserve(in_bytes));
-      TE_CUDA(cudaMemcpyAsync(c->stage[slot_in[k]].p, in[k], in_bytes, cudaMemcpyHostToDevice, c->stream));
+      if (wrapped) TE_CUDA(copy_wrapped((float*)c->stage[slot_in[k]].p, 0, const_cast<float*>(in[k]), g->rows, g->cols, sr, sc, 0, g->cols, true, c->stream));
+      else TE_CUDA(cudaMemcpyAsync(c->stage[slot_in[k]].p, in[k], in_bytes, cudaMemcpyHostToDevice, c->stream));
       in[k] = (const float*)c->stage[slot_in[k]].p;
     }
     for (int k = 0; k < 2; ++k) {
@@ -909,8 +928,13 @@ int te_footprint_polygon(te_ctx* c, const te_geometry* g, const te_slab* slab, c
   if (e != cudaSuccess) return fail(TE_ERR_CUDA, "polygon footprint launch failed: %s", cudaGetErrorString(e));
   c->launches += nl;
   if (memory == TE_MEM_HOST) {
-    TE_CUDA(cudaMemcpyAsync(out_x, o[0], out_bytes, cudaMemcpyDeviceToHost, c->stream));
-    TE_CUDA(cudaMemcpyAsync(out_rot, o[1], out_bytes, cudaMemcpyDeviceToHost, c->stream));
+    if (wrapped) {
+      TE_CUDA(copy_wrapped(o[0], 0, out_x, g->rows, g->cols, sr, sc, 0, g->cols, false, c->stream));
+      TE_CUDA(copy_wrapped(o[1], 0, out_rot, g->rows, g->cols, sr, sc, 0, g->cols, false, c->stream));
+    } else {
+      TE_CUDA(cudaMemcpyAsync(out_x, o[0], out_bytes, cudaMemcpyDeviceToHost, c->stream));
+      TE_CUDA(cudaMemcpyAsync(out_rot, o[1], out_bytes, cudaMemcpyDeviceToHost, c->stream));
+    }
     TE_CUDA(cudaStreamSynchronize(c->stream));
   }
   return TE_OK;
