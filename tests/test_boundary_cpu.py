@@ -28,7 +28,8 @@ def test_library_exports_every_declared_symbol(te):
 
 
 @pytest.mark.parametrize("rows,cols,nmaps,sms", [(8192, 8192, 1, 148), (2048, 2048, 1, 148), (4096, 4096, 1, 148), (512, 512, 256, 148),
-                                                  (192, 160, 1, 148), (60, 7, 1, 148), (8192, 2052, 1, 148), (1000, 333, 3, 132)])
+                                                  (192, 160, 1, 148), (60, 7, 1, 148), (8192, 2052, 1, 148), (1000, 333, 3, 132),
+                                                  (8192, 1024, 1, 148), (8192, 4096, 1, 148), (8192, 6000, 1, 148), (16384, 16384, 1, 148)])
 def test_fused_work_units_tile_every_map_exactly_once(te, rows, cols, nmaps, sms):
     """The fused kernel's queue of (level, map, segment, strip) units — decoded here the way the kernel decodes a unit id —
     covers every (map, strip, column) once, hands out longer segments first and ends on the unit count it reports."""
@@ -56,6 +57,20 @@ def test_fused_work_units_tile_every_map_exactly_once(te, rows, cols, nmaps, sms
     assert unit == plan["units"]
     assert (cover == 1).all()
     assert lens == sorted(lens, reverse=True) and min(lens) >= 8
+
+
+def test_fused_plan_shapes_of_the_bench_configurations(te):
+    """What plan_levels decides for the sizes the bench lines are quoted on (profiles/README.md, round 2): one long unit per warp
+    first for the big single map, one round of one segment length for small launches, the tapering plan in between."""
+    big = te.capi.fused_plan(8192, 8192, 1, 148)["levels"]
+    assert (big[0]["seg_len"], big[0]["nseg"]) == (512, 12) and big[1]["seg_len"] == 24 and big[2]["seg_len"] == 16
+    assert 137 * 12 <= 148 * 12                                    # at most one long unit per warp
+    slab = te.capi.fused_plan(8192, 1024, 1, 148)
+    assert slab["levels"][0]["seg_len"] == 88 and slab["units"] == 137 * 12 <= 148 * 12   # one round
+    small = te.capi.fused_plan(2048, 2048, 1, 148)
+    assert small["levels"][0]["seg_len"] == 44 and small["units"] <= 148 * 12
+    batch = te.capi.fused_plan(512, 512, 256, 148)["levels"]
+    assert batch[0]["seg_len"] == 80 and batch[1]["seg_len"] == 24  # many rounds: long segments first, short ones last
 
 
 def test_fused_plan_rejects_bad_sizes(te):
