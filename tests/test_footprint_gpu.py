@@ -202,6 +202,7 @@ def test_batched_circular_footprint_paths(te, ctx, oracle):
     dict(rows=160, cols=140, seed=61, res=0.02, yaw=0.7854),          # YAML footprint + robot.yaml yaw: 92 on-edge offsets at 0.02 m
     dict(rows=150, cols=133, seed=62, res=0.03, yaw=0.3, position=(57.25, -31.5)),
     dict(rows=96, cols=200, seed=63, res=0.02, yaw=1.5707963267948966, poly=[[0.5, 0.2], [0.1, -0.3], [-0.5, -0.2], [-0.4, 0.26], [0.0, 0.1]]),
+    dict(rows=640, cols=512, seed=64, res=0.02, yaw=0.7854),          # many tiles in both directions, ~1 s of oracle on the GPU box's cores
 ])
 def test_polygon_footprint_sweep_matches_oracle(te, ctx, oracle, case):
     """§8(f)-3: traversabilityFootprint(yaw) (TraversabilityMap.cpp:239-305, :592-645): traversability_x / traversability_rot."""
